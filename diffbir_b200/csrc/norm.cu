@@ -1,0 +1,298 @@
+// GroupNorm (32 groups) statistics + apply and LayerNorm, fp32 math, NHWC activations.
+//
+// GroupNorm replaces GroupNorm32 / Normalize (reference util.py:191-193 eps 1e-5,
+// attention.py:48-51 and vae.py:18-21 eps 1e-6). The input may be a *virtual concat* of two
+// NHWC tensors along C (UNet output blocks normalise cat([h, skip+control]),
+// controlnet.py:39-44); groups that straddle the boundary are handled because statistics
+// are first taken per channel. The apply pass writes the 16-bit tensor-core operand that the
+// implicit-GEMM convolution reads through TMA (optionally 2x nearest-upsampled:
+// unet.py:76-78, vae.py:37-40), fused with SiLU.
+//
+// LayerNorm replaces nn.LayerNorm in BasicTransformerBlock (attention.py:257-259) and
+// SwinIR (swinir.py:208,214,722,783), eps 1e-5, writing the 16-bit operand of the next GEMM.
+#include "common.cuh"
+#include "../../include/diffbir_b200.h"
+
+namespace {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_WARPS = GN_THREADS / 32;
+
+__device__ __forceinline__ const float* cat_ptr(const float* s1, const float* s2, int c1, int c2,
+                                                long long pix, int c) {
+  // element (pix, c) of the virtual concat [pix, c1 + c2]
+  return c < c1 ? s1 + pix * c1 + c : s2 + pix * c2 + (c - c1);
+}
+
+// Stage 1: per-channel sum / sum of squares over a chunk of pixels.
+// grid = (chunks, N). partial layout: [N][chunks][C][2].
+// The last CTA of each image (atomic ticket) folds the partials into per-group mean / rstd.
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int c1, int c2,
+                int hw, int pix_per_chunk, float* __restrict__ partial,
+                unsigned int* __restrict__ tickets, float* __restrict__ stats, float eps) {
+  const int C = c1 + c2;
+  const int n = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int chunks = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p_begin = chunk * pix_per_chunk;
+  const int p_end = min(hw, p_begin + pix_per_chunk);
+  __shared__ float s_part[GN_WARPS][128][2];
+  __shared__ bool s_last;
+  float* my_partial = partial + (static_cast<long long>(n) * chunks + chunk) * C * 2;
+
+  // channel slabs of 128 (one float4 per lane)
+  for (int cb = 0; cb < C; cb += 128) {
+    const int c = cb + lane * 4;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+      for (int p = p_begin + warp; p < p_end; p += GN_WARPS) {
+        const long long pix = static_cast<long long>(n) * hw + p;
+        // c1, c2 are multiples of 4, so a float4 never straddles the concat boundary
+        const float4 v = *reinterpret_cast<const float4*>(cat_ptr(s1, s2, c1, c2, pix, c));
+        sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
+        sq[0] += v.x * v.x; sq[1] += v.y * v.y; sq[2] += v.z * v.z; sq[3] += v.w * v.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s_part[warp][lane * 4 + j][0] = sum[j];
+      s_part[warp][lane * 4 + j][1] = sq[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 128 && cb + threadIdx.x < C) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < GN_WARPS; ++w) { a += s_part[w][threadIdx.x][0]; b += s_part[w][threadIdx.x][1]; }
+      my_partial[(cb + threadIdx.x) * 2 + 0] = a;
+      my_partial[(cb + threadIdx.x) * 2 + 1] = b;
+    }
+    __syncthreads();
+  }
+
+  // ---- last-CTA-of-the-image finalisation (deterministic: fixed summation order) ----
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[n], 1u);
+    s_last = (t == static_cast<unsigned int>(chunks) - 1);
+    if (s_last) tickets[n] = 0;   // self-reset for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int cpg = C / 32;
+  const float* img_partial = partial + static_cast<long long>(n) * chunks * C * 2;
+  for (int g = warp; g < 32; g += GN_WARPS) {
+    double a = 0.0, b = 0.0;
+    const int total = chunks * cpg;
+    for (int i = lane; i < total; i += 32) {
+      const int ch = i / cpg, cc = g * cpg + i % cpg;
+      const float* q = img_partial + (static_cast<long long>(ch) * C + cc) * 2;
+      a += static_cast<double>(__ldcg(q));
+      b += static_cast<double>(__ldcg(q + 1));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      const double cnt = static_cast<double>(hw) * cpg;
+      const double mean = a / cnt;
+      double var = b / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[(n * 32 + g) * 2 + 0] = static_cast<float>(mean);
+      stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+}
+
+// Stage 2: y = silu?(x * a[c] + b[c]) -> op16, optional 2x nearest upsample, optional raw copy.
+// grid = (pixel chunks, N)
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int c1, int c2,
+                int h, int w, const float* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int do_norm, int do_silu, int up,
+                op_t* __restrict__ out, op_t* __restrict__ out_raw, int pix_per_cta) {
+  extern __shared__ float s_ab[];   // [C][2]
+  const int C = c1 + c2;
+  const int n = blockIdx.y;
+  const int hw = h * w;
+  if (do_norm) {
+    const int cpg = C / 32;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const float mean = stats[(n * 32 + g) * 2], rstd = stats[(n * 32 + g) * 2 + 1];
+      const float a = gamma[c] * rstd;
+      s_ab[2 * c] = a;
+      s_ab[2 * c + 1] = beta[c] - mean * a;
+    }
+    __syncthreads();
+  }
+  const int V = C / 4;
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  const long long total = static_cast<long long>(p_end - p_begin) * V;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int p = p_begin + static_cast<int>(i / V);
+    const int c = static_cast<int>(i % V) * 4;
+    const long long pix = static_cast<long long>(n) * hw + p;
+    const float4 v = *reinterpret_cast<const float4*>(cat_ptr(s1, s2, c1, c2, pix, c));
+    float y[4] = {v.x, v.y, v.z, v.w};
+    uint2 raw;
+    raw.x = pack2(v.x, v.y); raw.y = pack2(v.z, v.w);
+    if (do_norm) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = y[j] * s_ab[2 * (c + j)] + s_ab[2 * (c + j) + 1];
+    }
+    if (do_silu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
+    }
+    uint2 o;
+    o.x = pack2(y[0], y[1]); o.y = pack2(y[2], y[3]);
+    if (up == 1) {
+      *reinterpret_cast<uint2*>(out + pix * C + c) = o;
+      if (out_raw) *reinterpret_cast<uint2*>(out_raw + pix * C + c) = raw;
+    } else {
+      const int py = p / w, px = p % w;
+      const int W2 = w * 2;
+      const long long base = (static_cast<long long>(n) * (h * 2) + py * 2) * W2 + px * 2;
+      *reinterpret_cast<uint2*>(out + (base) * C + c) = o;
+      *reinterpret_cast<uint2*>(out + (base + 1) * C + c) = o;
+      *reinterpret_cast<uint2*>(out + (base + W2) * C + c) = o;
+      *reinterpret_cast<uint2*>(out + (base + W2 + 1) * C + c) = o;
+    }
+  }
+}
+
+// LayerNorm over the last dim; one warp per row; C <= 1280, C % 4 == 0.
+// Output op16 with row stride ldo >= C; columns [C, ldo) are zero-filled (K padding).
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 op_t* __restrict__ out, long long ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  constexpr int MAXV = 10;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < C) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  s = warp_sum(s);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < C) {
+      const float a = v[i].x - mean, b = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + b * b) + (d * d + e * e);
+    }
+  }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / C + eps);
+  op_t* orow = out + row * ldo;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < C) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 b = *reinterpret_cast<const float4*>(beta + c);
+      uint2 o;
+      o.x = pack2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      o.y = pack2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      *reinterpret_cast<uint2*>(orow + c) = o;
+    } else if (c < ldo) {
+      *reinterpret_cast<uint2*>(orow + c) = make_uint2(0u, 0u);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t dbir_gn_workspace_floats(int32_t n, int32_t hw, int32_t c) {
+  // partials [n][chunks][c][2] with chunks <= 512, plus tickets
+  int chunks = (hw + 31) / 32;
+  if (chunks > 512) chunks = 512;
+  return static_cast<int64_t>(n) * chunks * c * 2 + 64 + n;
+}
+
+static int gn_chunks(int n, int hw, int* pix_per_chunk) {
+  // aim for >= 2 waves of CTAs, at least 8 pixels (one per warp) per chunk
+  const int target = 2 * dbir_sm_count();
+  int chunks = (target + n - 1) / n;
+  int ppc = (hw + chunks - 1) / chunks;
+  if (ppc < 8) ppc = 8;
+  chunks = (hw + ppc - 1) / ppc;
+  if (chunks > 512) { chunks = 512; ppc = (hw + chunks - 1) / chunks; chunks = (hw + ppc - 1) / ppc; }
+  *pix_per_chunk = ppc;
+  return chunks;
+}
+
+extern "C" int dbir_gn_stats(const float* src1, const float* src2, int32_t c1, int32_t c2,
+                             int32_t n, int32_t hw, float eps, float* stats, float* workspace,
+                             void* stream) {
+  const int C = c1 + c2;
+  DBIR_REQUIRE(src1 && stats && workspace, "dbir_gn_stats: null pointer");
+  DBIR_REQUIRE(c1 % 4 == 0 && c2 % 4 == 0 && C % 32 == 0, "dbir_gn_stats: bad channels %d+%d", c1, c2);
+  DBIR_REQUIRE(c2 == 0 || src2, "dbir_gn_stats: src2 missing");
+  int ppc;
+  const int chunks = gn_chunks(n, hw, &ppc);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
+  float* partial = workspace + 64 + ((n + 3) / 4) * 4;
+  gn_stats_kernel<<<dim3(chunks, n), GN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src1, src2, c1, c2, hw, ppc, partial, tickets, stats, eps);
+  DBIR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, int32_t c2,
+                             int32_t n, int32_t h, int32_t w, const float* stats,
+                             const float* gamma, const float* beta, int32_t do_norm,
+                             int32_t do_silu, int32_t upsample, void* out, void* out_raw,
+                             void* stream) {
+  const int C = c1 + c2;
+  DBIR_REQUIRE(src1 && out, "dbir_gn_apply: null pointer");
+  DBIR_REQUIRE(c1 % 4 == 0 && c2 % 4 == 0, "dbir_gn_apply: channels must be multiples of 4");
+  DBIR_REQUIRE(!do_norm || (stats && gamma && beta && C % 32 == 0), "dbir_gn_apply: norm args");
+  DBIR_REQUIRE(upsample == 1 || upsample == 2, "dbir_gn_apply: upsample must be 1 or 2");
+  DBIR_REQUIRE(!(upsample == 2 && out_raw), "dbir_gn_apply: raw copy unsupported with upsample");
+  const int hw = h * w;
+  const int target = 4 * dbir_sm_count();
+  int ctas = (target + n - 1) / n;
+  int ppc = (hw + ctas - 1) / ctas;
+  if (ppc < 1) ppc = 1;
+  ctas = (hw + ppc - 1) / ppc;
+  const size_t smem = do_norm ? static_cast<size_t>(C) * 2 * sizeof(float) : 0;
+  gn_apply_kernel<<<dim3(ctas, n), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src1, src2, c1, c2, h, w, stats, gamma, beta, do_norm, do_silu, upsample,
+      reinterpret_cast<op_t*>(out), reinterpret_cast<op_t*>(out_raw), ppc);
+  DBIR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t c,
+                              const float* gamma, const float* beta, float eps, void* out,
+                              int64_t ldo, void* stream) {
+  DBIR_REQUIRE(x && gamma && beta && out, "dbir_layernorm: null pointer");
+  DBIR_REQUIRE(c % 4 == 0 && c <= 1280 && ldo >= c && ldo % 4 == 0 && ldo <= 1280,
+               "dbir_layernorm: unsupported width %d (ldo %lld)", c, (long long)ldo);
+  const int rows_per_cta = 8;
+  layernorm_kernel<<<(rows + rows_per_cta - 1) / rows_per_cta, 256, 0,
+                     reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, ldx, rows, c, gamma, beta, eps, reinterpret_cast<op_t*>(out), ldo);
+  DBIR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
