@@ -1,0 +1,267 @@
+// Flash attention for head_dim 64 on tcgen05 / TMEM (self- and cross-attention of the
+// SpatialTransformer: reference attention.py:189-216 `F.scaled_dot_product_attention`,
+// with the head split/merge copies of :196-214 folded into TMA coordinates).
+//
+//   O[b, i, h*64:(h+1)*64] = softmax_j(Q_h[i] . K_h[j] / 8) V_h[j]
+//
+// Q/K/V are 16-bit matrices [B, S, ld] (any row stride / column offset, e.g. slices of a fused
+// QKV projection). One CTA = one (128-query tile, head, batch):
+//   warp 0   TMA producer   (Q once, K/V tiles of 128 keys, 2 stages)
+//   warp 1   MMA issuer     S = Q K^T -> TMEM[0:128), PV -> TMEM[128:192)
+//   warps 2-5 softmax       thread == query row: online softmax in fp32 with exp2,
+//                            P (16-bit) -> swizzled smem, running O kept in registers.
+// Two CTAs are resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax
+// overlaps the other's MMAs.
+#include "common.cuh"
+#include "../../include/diffbir_b200.h"
+
+namespace {
+
+constexpr int TQ = 128;      // queries per CTA
+constexpr int TK = 128;      // keys per tile
+constexpr int DH = 64;
+constexpr int KV_STAGES = 2;
+constexpr int TILE_BYTES = 128 * DH * 2;   // 16 KB
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TM_S = 0, TM_O = 128;
+
+struct AttnParams {
+  int sq, skv, heads;
+  void* out;
+  long long ldo;       // elements per output row
+  float scale_log2;    // dh^-0.5 * log2(e)
+};
+
+struct __align__(8) AttnBarriers {
+  uint64_t q_full;
+  uint64_t kv_full[KV_STAGES];
+  uint64_t kv_empty[KV_STAGES];
+  uint64_t s_full;
+  uint64_t p_full;
+  uint64_t o_full;
+  uint32_t tmem_slot;
+};
+
+constexpr int ATTN_SMEM = TILE_BYTES * (1 + 2 * KV_STAGES + 2) + 256;
+
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;
+  uint8_t* sP = sV + KV_STAGES * TILE_BYTES;            // two [128 x 64] swizzled sub-tiles
+  AttnBarriers* bar = reinterpret_cast<AttnBarriers*>(sP + 2 * TILE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = (p.skv + TK - 1) / TK;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("dbir attention: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bar->q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&bar->kv_full[s], 1); mbar_init(&bar->kv_empty[s], 1); }
+    mbar_init(&bar->s_full, 1);
+    mbar_init(&bar->p_full, 128);
+    mbar_init(&bar->o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&bar->tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bar->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bar->q_full, TILE_BYTES);
+      tma_load_3d(sQ, &tma_q, &bar->q_full, head * DH, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(&bar->kv_empty[s], ph ^ 1);
+        mbar_expect_tx(&bar->kv_full[s], 2 * TILE_BYTES);
+        tma_load_3d(sK + s * TILE_BYTES, &tma_k, &bar->kv_full[s], head * DH, j * TK, b);
+        tma_load_3d(sV + s * TILE_BYTES, &tma_v, &bar->kv_full[s], head * DH, j * TK, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(TK, 0, 0);   // S[128 x 128]: Q, K both K-major
+      constexpr uint32_t idesc_o = umma_idesc(DH, 0, 1);   // O[128 x 64]: P K-major, V MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      mbar_wait(&bar->q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        const uint32_t k_addr = smem_u32(sK + s * TILE_BYTES);
+        const uint32_t v_addr = smem_u32(sV + s * TILE_BYTES);
+        mbar_wait(&bar->kv_full[s], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_f16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32),
+                   idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&bar->s_full);
+        // P(j) in smem (written by the softmax warps) x V(j)
+        mbar_wait(&bar->p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k)
+          umma_f16(tmem_base + TM_O,
+                   umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
+                   umma_desc_sw128(v_addr + k * 16 * 128), idesc_o, k != 0 ? 1u : 0u);
+        umma_commit(&bar->o_full);
+        umma_commit(&bar->kv_empty[s]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // query row in the tile == TMEM lane
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TM_S;
+    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TM_O;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o_acc[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) o_acc[c] = 0.f;
+    uint8_t* p_row = sP + r * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int valid = min(TK, p.skv - j * TK);
+      mbar_wait(&bar->s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float m_tile = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TK; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(t_s + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < valid) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      const float alpha = exp2f((m_run - m_new) * sl2);
+      const float mb = m_new * sl2;
+      float l_tile = 0.f;
+      // P(j-1) must have been consumed by PV(j-1) before it is overwritten: o_full(j-1) was
+      // awaited below in the previous iteration.
+#pragma unroll 1
+      for (int c0 = 0; c0 < TK; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(t_s + c0, v);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = exp2f(__uint_as_float(v[i]) * sl2 - mb);
+          e[i] = (c0 + i < valid) ? x : 0.f;
+          l_tile += e[i];
+        }
+        // 32 columns = 4 chunks of 16 bytes inside sub-tile c0/64
+        uint8_t* base = p_row + (c0 >> 6) * TILE_BYTES;
+        const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 t;
+          t.x = pack2(e[ch * 8 + 0], e[ch * 8 + 1]);
+          t.y = pack2(e[ch * 8 + 2], e[ch * 8 + 3]);
+          t.z = pack2(e[ch * 8 + 4], e[ch * 8 + 5]);
+          t.w = pack2(e[ch * 8 + 6], e[ch * 8 + 7]);
+          *reinterpret_cast<uint4*>(base + (((chunk0 + ch) ^ sw) << 4)) = t;
+        }
+      }
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&bar->p_full);
+      // O(j) partial
+      mbar_wait(&bar->o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < DH; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(t_o + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = o_acc[c0 + i] * alpha + __uint_as_float(v[i]);
+      }
+    }
+    tc_fence_before();
+    // epilogue: normalise and store 64 x 16-bit = 128 bytes per row
+    const int qi = q0 + r;
+    if (qi < p.sq) {
+      const float inv = 1.0f / l_run;
+      op_t* o = reinterpret_cast<op_t*>(p.out) + (static_cast<long long>(b) * p.sq + qi) * p.ldo + head * DH;
+#pragma unroll
+      for (int c = 0; c < DH; c += 8) {
+        uint4 t;
+        t.x = pack2(o_acc[c] * inv, o_acc[c + 1] * inv);
+        t.y = pack2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+        t.z = pack2(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
+        t.w = pack2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(o + c) = t;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+int make_qkv_map(CUtensorMap* m, const void* base, int batch, int s, long long ld, int width) {
+  uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(s),
+                      static_cast<uint64_t>(batch)};
+  uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(s) * ld * 2};
+  uint32_t box[3] = {DH, 128, 1};
+  return dbir_make_tmap(m, base, 3, dims, strides, box, 2, 1);
+}
+
+}  // namespace
+
+extern "C" int dbir_attention(const void* q, const void* k, const void* v, void* out,
+                              int32_t batch, int32_t heads, int32_t sq, int32_t skv,
+                              int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, void* stream) {
+  DBIR_REQUIRE(q && k && v && out, "dbir_attention: null pointer");
+  DBIR_REQUIRE(batch > 0 && heads > 0 && sq > 0 && skv > 0, "dbir_attention: bad shape");
+  DBIR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+               "dbir_attention: row strides must be multiples of 8 elements");
+  CUtensorMap mq, mk, mv;
+  const int width = heads * DH;
+  if (make_qkv_map(&mq, q, batch, sq, ldq, width)) return -3;
+  if (make_qkv_map(&mk, k, batch, skv, ldk, width)) return -3;
+  if (make_qkv_map(&mv, v, batch, skv, ldv, width)) return -3;
+  AttnParams p;
+  p.sq = sq; p.skv = skv; p.heads = heads;
+  p.out = out; p.ldo = ldo;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  static bool configured = false;
+  if (!configured) {
+    DBIR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ATTN_SMEM));
+    configured = true;
+  }
+  dim3 grid((sq + TQ - 1) / TQ, heads, batch);
+  attn_fwd_kernel<<<grid, 192, ATTN_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mq, mk, mv, p);
+  DBIR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -44,6 +44,9 @@ struct GemmParams {
   int act;                 // 0 none, 1 gelu(erf), 2 leaky relu (slope in act_param), 3 silu
   float act_param;
   int geglu;               // 1: tile holds [BN/2 values | BN/2 gates]; output width N/2
+  int bias_per_row;        // bias indexed by output row instead of column
+  void* out2;              // optional second copy of the result as op16 [rows, ldo2]
+  long long ldo2;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float prm) {
@@ -173,8 +176,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
         if (p.bias) {
+          if (p.bias_per_row) {
+            const float bv = __ldg(p.bias + out_row);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gc0 + j);
+            for (int j = 0; j < 32; ++j) v[j] += bv;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gc0 + j);
+          }
         }
         if (p.rowvec) {
           const float* rv = p.rowvec + static_cast<long long>(vec_idx) * p.N + gc0;
@@ -214,6 +223,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         } else {
           op_t* o = reinterpret_cast<op_t*>(p.out) + out_row * p.ldo + gc0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 t;
+              t.x = pack2(v[j], v[j + 1]); t.y = pack2(v[j + 2], v[j + 3]);
+              t.z = pack2(v[j + 4], v[j + 5]); t.w = pack2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = t;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = f2op(v[j]);
+          }
+        }
+        if (p.out2) {
+          op_t* o = reinterpret_cast<op_t*>(p.out2) + out_row * p.ldo2 + gc0;
           if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -336,6 +360,7 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
   p.rows_per_vec = a->rows_per_vec > 0 ? a->rows_per_vec : a->M;
   p.residual = a->residual; p.ldr = a->ldr;
   p.alpha = a->alpha; p.act = a->act; p.act_param = a->act_param; p.geglu = a->geglu;
+  p.bias_per_row = a->bias_per_row; p.out2 = a->out2; p.ldo2 = a->ldo2;
   if (a->geglu)
     DBIR_REQUIRE(a->force_bn >= 64 && a->N % a->force_bn == 0,
                  "dbir_gemm: GEGLU needs force_bn (>= 64) dividing N (weights are packed per tile)");

@@ -169,10 +169,11 @@ gn_apply_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
 
 // LayerNorm over the last dim; one warp per row; C <= 1280, C % 4 == 0.
 // Output op16 with row stride ldo >= C; columns [C, ldo) are zero-filled (K padding).
+template <bool F32OUT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                 op_t* __restrict__ out, long long ldo) {
+                 void* __restrict__ out_v, long long ldo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -203,19 +204,24 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C,
   }
   q = warp_sum(q);
   const float rstd = rsqrtf(q / C + eps);
-  op_t* orow = out + row * ldo;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = (lane + 32 * i) * 4;
     if (c < C) {
       const float4 g = *reinterpret_cast<const float4*>(gamma + c);
       const float4 b = *reinterpret_cast<const float4*>(beta + c);
-      uint2 o;
-      o.x = pack2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-      o.y = pack2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-      *reinterpret_cast<uint2*>(orow + c) = o;
+      const float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (F32OUT) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_v) + row * ldo + c) = make_float4(y0, y1, y2, y3);
+      } else {
+        uint2 o;
+        o.x = pack2(y0, y1); o.y = pack2(y2, y3);
+        *reinterpret_cast<uint2*>(reinterpret_cast<op_t*>(out_v) + row * ldo + c) = o;
+      }
     } else if (c < ldo) {
-      *reinterpret_cast<uint2*>(orow + c) = make_uint2(0u, 0u);
+      if (F32OUT) *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_v) + row * ldo + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      else *reinterpret_cast<uint2*>(reinterpret_cast<op_t*>(out_v) + row * ldo + c) = make_uint2(0u, 0u);
     }
   }
 }
@@ -223,10 +229,10 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C,
 }  // namespace
 
 extern "C" int64_t dbir_gn_workspace_floats(int32_t n, int32_t hw, int32_t c) {
-  // partials [n][chunks][c][2] with chunks <= 512, plus tickets
-  int chunks = (hw + 31) / 32;
+  // partials [n][chunks][c][2] with chunks <= min(512, ceil(hw / 8)), plus tickets
+  int chunks = (hw + 7) / 8;
   if (chunks > 512) chunks = 512;
-  return static_cast<int64_t>(n) * chunks * c * 2 + 64 + n;
+  return static_cast<int64_t>(n) * chunks * c * 2 + 64 + ((n + 3) / 4) * 4 + 64;
 }
 
 static int gn_chunks(int n, int hw, int* pix_per_chunk) {
@@ -285,14 +291,18 @@ extern "C" int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, i
 
 extern "C" int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t c,
                               const float* gamma, const float* beta, float eps, void* out,
-                              int64_t ldo, void* stream) {
+                              int64_t ldo, int32_t out_kind, void* stream) {
   DBIR_REQUIRE(x && gamma && beta && out, "dbir_layernorm: null pointer");
   DBIR_REQUIRE(c % 4 == 0 && c <= 1280 && ldo >= c && ldo % 4 == 0 && ldo <= 1280,
                "dbir_layernorm: unsupported width %d (ldo %lld)", c, (long long)ldo);
   const int rows_per_cta = 8;
-  layernorm_kernel<<<(rows + rows_per_cta - 1) / rows_per_cta, 256, 0,
-                     reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, ldx, rows, c, gamma, beta, eps, reinterpret_cast<op_t*>(out), ldo);
+  const int grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  if (out_kind == 0)
+    layernorm_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, ldx, rows, c, gamma, beta, eps, out, ldo);
+  else
+    layernorm_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, ldx, rows, c, gamma, beta, eps, out, ldo);
   DBIR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,369 @@
+"""ControlNet + ControlledUnetModel forward on the sm_100a kernels.
+
+Replaces ControlLDM.forward (reference model/cldm.py:160-172), i.e. ControlNet.forward
+(model/controlnet.py:314-328) and ControlledUnetModel.forward (model/controlnet.py:18-47),
+for the SD-2.1 configuration of configs/inference/cldm.yaml (or any channel set that is a
+multiple of 64 with 64-wide heads).
+
+Data layout in HBM: activations NHWC; the residual stream / skip tensors / eps are fp32;
+every tensor-core operand (normalised activations, Q/K/V, attention output, GEGLU hidden) is
+16-bit (lib.operand_dtype()) and exists only between its producer and the GEMM that eats it.
+
+Execution order inside one forward: UNet encoder + middle (produces the skips hs[i]), then
+ControlNet, whose zero-conv epilogues write  hs[i] += scale_i * (W h + b)  in place
+(fusing cldm.py:164 and controlnet.py:36-43 into the GEMM), then the UNet decoder, which reads
+cat([h, hs[i]]) as a *virtual* concat (GroupNorm statistics + operand pass read both sources).
+
+What is hoisted out of the per-step path (constant across sampler steps):
+  * text K/V projections of every cross-attention (attention.py:192-193) -> set_context()
+  * time-embedding MLP and the per-ResBlock emb_layers (unet.py:616-617, 166-172)
+    -> set_timesteps() builds a table indexed by step.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from .. import arch, lib
+from .common import Workspace, f32, geglu_tile, op16, pack_conv3x3, pack_geglu, pack_linear
+
+HEAD_DIM = 64
+
+
+class _Net:
+    """Packed weights of one UNet-like network (UNet or ControlNet)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: dict, controlnet: bool, device):
+        self.cfg = cfg
+        self.plan = arch.unet_plan(cfg, controlnet)
+        self.controlnet = controlnet
+        self.dev = device
+        self.w: Dict[str, torch.Tensor] = {}
+        shapes = arch.unet_shapes(cfg, controlnet)
+        missing = [k for k in shapes if k not in sd]
+        if missing:
+            raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]}")
+        for k, shp in shapes.items():
+            if tuple(sd[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: checkpoint shape {tuple(sd[k].shape)} != expected {shp}")
+        self.res_layers: List[arch.Layer] = []
+        self.attn_layers: List[arch.Layer] = []
+        for blk in self.plan.input_blocks + [self.plan.middle] + self.plan.output_blocks:
+            for l in blk.layers:
+                self._pack_layer(sd, l)
+        w = self.w
+        for nm in ("time_embed.0", "time_embed.2"):
+            w[nm + ".weight"] = f32(sd[nm + ".weight"], device)
+            w[nm + ".bias"] = f32(sd[nm + ".bias"], device)
+        if controlnet:
+            for i in range(len(self.plan.input_blocks)):
+                w[f"zero_convs.{i}.w"] = pack_linear(sd[f"zero_convs.{i}.0.weight"], device)
+                w[f"zero_convs.{i}.b"] = f32(sd[f"zero_convs.{i}.0.bias"], device)
+            w["middle_block_out.w"] = pack_linear(sd["middle_block_out.0.weight"], device)
+            w["middle_block_out.b"] = f32(sd["middle_block_out.0.bias"], device)
+        else:
+            w["out.0.weight"] = f32(sd["out.0.weight"], device)
+            w["out.0.bias"] = f32(sd["out.0.bias"], device)
+            ow = sd["out.2.weight"]
+            w["out.2.weight"] = f32(ow.permute(0, 2, 3, 1).reshape(ow.shape[0], -1), device)
+            w["out.2.bias"] = f32(sd["out.2.bias"], device)
+
+    def _pack_layer(self, sd, l: arch.Layer):
+        w, p, dev = self.w, l.prefix, self.dev
+        if l.kind == "conv_in":
+            cw = sd[p + "weight"]                           # [Cout, Cin, 3, 3] -> [9*Cin, Cout]
+            w[p + "w"] = f32(cw.permute(2, 3, 1, 0).reshape(-1, cw.shape[0]), dev)
+            w[p + "b"] = f32(sd[p + "bias"], dev)
+        elif l.kind == "res":
+            self.res_layers.append(l)
+            for nm in ("in_layers.0", "out_layers.0"):
+                w[p + nm + ".weight"] = f32(sd[p + nm + ".weight"], dev)
+                w[p + nm + ".bias"] = f32(sd[p + nm + ".bias"], dev)
+            w[p + "conv1.w"] = pack_conv3x3(sd[p + "in_layers.2.weight"], dev)
+            w[p + "conv1.b"] = f32(sd[p + "in_layers.2.bias"], dev)
+            w[p + "conv2.w"] = pack_conv3x3(sd[p + "out_layers.3.weight"], dev)
+            w[p + "conv2.b"] = f32(sd[p + "out_layers.3.bias"], dev)
+            w[p + "emb.w"] = f32(sd[p + "emb_layers.1.weight"], dev)
+            w[p + "emb.b"] = f32(sd[p + "emb_layers.1.bias"], dev)
+            if l.cin != l.cout:
+                w[p + "skip.w"] = pack_linear(sd[p + "skip_connection.weight"], dev)
+                w[p + "skip.b"] = f32(sd[p + "skip_connection.bias"], dev)
+        elif l.kind == "attn":
+            self.attn_layers.append(l)
+            c = l.cin
+            q = p + "transformer_blocks.0."
+            for nm in ("norm",):
+                w[p + nm + ".weight"] = f32(sd[p + nm + ".weight"], dev)
+                w[p + nm + ".bias"] = f32(sd[p + nm + ".bias"], dev)
+            w[p + "proj_in.w"] = pack_linear(sd[p + "proj_in.weight"], dev)
+            w[p + "proj_in.b"] = f32(sd[p + "proj_in.bias"], dev)
+            w[p + "proj_out.w"] = pack_linear(sd[p + "proj_out.weight"], dev)
+            w[p + "proj_out.b"] = f32(sd[p + "proj_out.bias"], dev)
+            for nm in ("norm1", "norm2", "norm3"):
+                w[q + nm + ".weight"] = f32(sd[q + nm + ".weight"], dev)
+                w[q + nm + ".bias"] = f32(sd[q + nm + ".bias"], dev)
+            w[q + "qkv.w"] = op16(torch.cat([sd[q + "attn1.to_q.weight"], sd[q + "attn1.to_k.weight"],
+                                             sd[q + "attn1.to_v.weight"]], 0), dev)
+            w[q + "o1.w"] = pack_linear(sd[q + "attn1.to_out.0.weight"], dev)
+            w[q + "o1.b"] = f32(sd[q + "attn1.to_out.0.bias"], dev)
+            w[q + "q2.w"] = pack_linear(sd[q + "attn2.to_q.weight"], dev)
+            w[q + "kv2.w"] = op16(torch.cat([sd[q + "attn2.to_k.weight"], sd[q + "attn2.to_v.weight"]], 0), dev)
+            w[q + "o2.w"] = pack_linear(sd[q + "attn2.to_out.0.weight"], dev)
+            w[q + "o2.b"] = f32(sd[q + "attn2.to_out.0.bias"], dev)
+            bn = geglu_tile(c)
+            w[q + "ff1.w"], w[q + "ff1.b"] = pack_geglu(sd[q + "ff.net.0.proj.weight"],
+                                                        sd[q + "ff.net.0.proj.bias"], bn, dev)
+            w[q + "ff2.w"] = pack_linear(sd[q + "ff.net.2.weight"], dev)
+            w[q + "ff2.b"] = f32(sd[q + "ff.net.2.bias"], dev)
+        elif l.kind == "down":
+            w[p + "w"] = pack_conv3x3(sd[p + "op.weight"], dev)
+            w[p + "b"] = f32(sd[p + "op.bias"], dev)
+        elif l.kind == "up":
+            w[p + "w"] = pack_conv3x3(sd[p + "conv.weight"], dev)
+            w[p + "b"] = f32(sd[p + "conv.bias"], dev)
+
+
+class CldmEngine:
+    def __init__(self, unet_sd, controlnet_sd, unet_cfg: dict = None, controlnet_cfg: dict = None,
+                 device="cuda"):
+        self.dev = torch.device(device)
+        unet_cfg = dict(arch.UNET_CFG if unet_cfg is None else unet_cfg)
+        controlnet_cfg = dict(arch.CONTROLNET_CFG if controlnet_cfg is None else controlnet_cfg)
+        self.unet = _Net(unet_sd, unet_cfg, False, self.dev)
+        self.cnet = _Net(controlnet_sd, controlnet_cfg, True, self.dev)
+        self.mc = unet_cfg["model_channels"]
+        self.ctx_dim = unet_cfg["context_dim"]
+        self.ws = Workspace(self.dev)
+        self.op_dtype = lib.operand_dtype()
+        self.kv: Dict[str, torch.Tensor] = {}      # per attention layer: op16 [nb*77, 2C]
+        self.ctx_len = 0
+        self.emb_table: Optional[torch.Tensor] = None
+        self.emb_offsets: Dict[str, int] = {}
+        self._nb = 0
+
+    # ------------------------------------------------------------------ hoisted work
+    def set_context(self, c_txt: torch.Tensor):
+        """c_txt fp32 [nb, L, ctx_dim] -> K/V of every cross-attention, op16 [nb*L, 2C]."""
+        nb, L, d = c_txt.shape
+        ctx16 = c_txt.to(self.dev).reshape(nb * L, d).to(self.op_dtype).contiguous()
+        self.ctx_len = L
+        self._nb = nb
+        for net, tag in ((self.unet, "u"), (self.cnet, "c")):
+            for l in net.attn_layers:
+                q = l.prefix + "transformer_blocks.0."
+                key = tag + l.prefix
+                buf = self.kv.get(key)
+                if buf is None or buf.shape[0] != nb * L:
+                    buf = torch.empty(nb * L, 2 * l.cin, dtype=self.op_dtype, device=self.dev)
+                    self.kv[key] = buf
+                lib.gemm(ctx16, net.w[q + "kv2.w"], buf, M=nb * L, N=2 * l.cin, K=d)
+
+    def set_timesteps(self, timesteps: Sequence[int], nb: int):
+        """Time-embedding MLP + emb_layers of every ResBlock for every sampler step.
+        Table layout: [steps][ per ResBlock r: nb x Cout_r ] fp32 (rows replicated over the
+        batch so each step needs a single device-to-device copy)."""
+        S = len(timesteps)
+        t = torch.tensor([float(x) for x in timesteps], dtype=torch.float32, device=self.dev)
+        offs, total = {}, 0
+        for net, tag in ((self.unet, "u"), (self.cnet, "c")):
+            for l in net.res_layers:
+                offs[tag + l.prefix] = total
+                total += nb * l.cout
+        table = torch.empty(S, total, dtype=torch.float32, device=self.dev)
+        emb_dim = 4 * self.mc
+        for net, tag in ((self.unet, "u"), (self.cnet, "c")):
+            te = torch.empty(S, self.mc, dtype=torch.float32, device=self.dev)
+            lib.timestep_embedding(t, S, self.mc, te)
+            h1 = torch.empty(S, emb_dim, dtype=torch.float32, device=self.dev)
+            lib.linear_f32(te, self.mc, S, self.mc, net.w["time_embed.0.weight"],
+                           net.w["time_embed.0.bias"], emb_dim, h1, emb_dim, silu_out=True)
+            emb = torch.empty(S, emb_dim, dtype=torch.float32, device=self.dev)
+            lib.linear_f32(h1, emb_dim, S, emb_dim, net.w["time_embed.2.weight"],
+                           net.w["time_embed.2.bias"], emb_dim, emb, emb_dim)
+            tmp = torch.empty(S, max(l.cout for l in net.res_layers), dtype=torch.float32, device=self.dev)
+            for l in net.res_layers:
+                o = offs[tag + l.prefix]
+                y = tmp[:, : l.cout]
+                lib.linear_f32(emb, emb_dim, S, emb_dim, net.w[l.prefix + "emb.w"],
+                               net.w[l.prefix + "emb.b"], l.cout, y, tmp.shape[1], silu_in=True)
+                table[:, o:o + nb * l.cout] = y.repeat(1, nb)
+        self.emb_table = table
+        self.emb_offsets = offs
+        self.emb_nb = nb
+        self.emb_cur = torch.empty(total, dtype=torch.float32, device=self.dev)
+        self.timesteps = list(timesteps)
+
+    def load_step(self, step_idx: int):
+        """Selects the time embedding of sampler step `step_idx` (one D2D copy, outside graphs)."""
+        self.emb_cur.copy_(self.emb_table[step_idx])
+
+    def _emb(self, tag: str, l: arch.Layer, nb: int) -> torch.Tensor:
+        o = self.emb_offsets[tag + l.prefix]
+        return self.emb_cur[o:o + nb * l.cout]
+
+    # ------------------------------------------------------------------ blocks
+    def _gn(self, src1, src2, c1, c2, nb, h, w, eps, gamma, beta, out16, silu, out_raw=None):
+        ws = self.ws
+        stats = ws.get("gn_stats", (nb * 64,), torch.float32)
+        wsp = ws.get("gn_ws", (lib.gn_workspace_floats(nb, h * w, c1 + c2),), torch.float32, zero=True)
+        lib.gn_stats(src1, src2, c1, c2, nb, h * w, eps, stats, wsp)
+        lib.gn_apply(src1, src2, c1, c2, nb, h, w, stats, gamma, beta, out16, norm=True, silu=silu,
+                     out_raw=out_raw)
+
+    def _res(self, net: _Net, tag: str, l: arch.Layer, src1, src2, c1, c2, nb, h, w, out):
+        """ResBlock._forward (unet.py:203-223): out may alias src1 when c2 == 0."""
+        ws, W, p = self.ws, net.w, l.prefix
+        cin, cout, M = c1 + c2, l.cout, nb * h * w
+        a16 = ws.get("res_a16", (M, cin), self.op_dtype)
+        raw16 = ws.get("res_raw16", (M, cin), self.op_dtype) if cin != cout else None
+        self._gn(src1, src2, c1, c2, nb, h, w, 1e-5, W[p + "in_layers.0.weight"],
+                 W[p + "in_layers.0.bias"], a16, True, out_raw=raw16)
+        h1 = ws.get("res_h1", (M, cout), torch.float32)
+        lib.gemm(a16, W[p + "conv1.w"], h1, M=M, N=cout, K=9 * cin, bias=W[p + "conv1.b"],
+                 rowvec=self._emb(tag, l, nb), conv=(nb, h, w, cin, 3))
+        b16 = ws.get("res_b16", (M, cout), self.op_dtype)
+        self._gn(h1, None, cout, 0, nb, h, w, 1e-5, W[p + "out_layers.0.weight"],
+                 W[p + "out_layers.0.bias"], b16, True)
+        if cin != cout:
+            skip = ws.get("res_skip", (M, cout), torch.float32)
+            lib.gemm(raw16, W[p + "skip.w"], skip, M=M, N=cout, K=cin, bias=W[p + "skip.b"])
+            res = skip
+        else:
+            res = src1
+        lib.gemm(b16, W[p + "conv2.w"], out, M=M, N=cout, K=9 * cout, bias=W[p + "conv2.b"],
+                 residual=res, conv=(nb, h, w, cout, 3))
+
+    def _attn(self, net: _Net, tag: str, l: arch.Layer, x, nb, h, w):
+        """SpatialTransformer.forward, in place on x (fp32 NHWC [nb,h,w,C]) — attention.py:334-353."""
+        ws, W, p = self.ws, net.w, l.prefix
+        q = p + "transformer_blocks.0."
+        c, M, hw = l.cin, nb * h * w, h * w
+        heads = c // HEAD_DIM
+        a16 = ws.get("at_a16", (M, c), self.op_dtype)
+        self._gn(x, None, c, 0, nb, h, w, 1e-6, W[p + "norm.weight"], W[p + "norm.bias"], a16, False)
+        t = ws.get("at_t", (M, c), torch.float32)
+        lib.gemm(a16, W[p + "proj_in.w"], t, M=M, N=c, K=c, bias=W[p + "proj_in.b"])
+        # self-attention
+        lib.layernorm(t, c, M, c, W[q + "norm1.weight"], W[q + "norm1.bias"], a16, c)
+        qkv = ws.get("at_qkv", (M, 3 * c), self.op_dtype)
+        lib.gemm(a16, W[q + "qkv.w"], qkv, M=M, N=3 * c, K=c)
+        att = ws.get("at_o16", (M, c), self.op_dtype)
+        lib.attention(qkv, qkv[:, c:], qkv[:, 2 * c:], att, batch=nb, heads=heads, sq=hw, skv=hw,
+                      ldq=3 * c, ldk=3 * c, ldv=3 * c, ldo=c)
+        lib.gemm(att, W[q + "o1.w"], t, M=M, N=c, K=c, bias=W[q + "o1.b"], residual=t)
+        # cross-attention on the (pre-projected) text context
+        lib.layernorm(t, c, M, c, W[q + "norm2.weight"], W[q + "norm2.bias"], a16, c)
+        q16 = ws.get("at_q16", (M, c), self.op_dtype)
+        lib.gemm(a16, W[q + "q2.w"], q16, M=M, N=c, K=c)
+        kv = self.kv[tag + l.prefix]
+        lib.attention(q16, kv, kv[:, c:], att, batch=nb, heads=heads, sq=hw, skv=self.ctx_len,
+                      ldq=c, ldk=2 * c, ldv=2 * c, ldo=c)
+        lib.gemm(att, W[q + "o2.w"], t, M=M, N=c, K=c, bias=W[q + "o2.b"], residual=t)
+        # GEGLU feed-forward
+        lib.layernorm(t, c, M, c, W[q + "norm3.weight"], W[q + "norm3.bias"], a16, c)
+        ffh = ws.get("at_ffh", (M, 4 * c), self.op_dtype)
+        lib.gemm(a16, W[q + "ff1.w"], ffh, M=M, N=8 * c, K=c, bias=W[q + "ff1.b"], geglu=True,
+                 force_bn=geglu_tile(c))
+        lib.gemm(ffh, W[q + "ff2.w"], a16, M=M, N=c, K=4 * c, bias=W[q + "ff2.b"], residual=t)
+        lib.gemm(a16, W[p + "proj_out.w"], x, M=M, N=c, K=c, bias=W[p + "proj_out.b"], residual=x)
+
+    def _down(self, net: _Net, l: arch.Layer, x, nb, h, w, out):
+        c, ho, wo = l.cin, h // 2, w // 2
+        col = self.ws.get("down_col", (nb * ho * wo, 9 * c), self.op_dtype)
+        lib.im2col_s2(x, nb, h, w, c, 1, col)
+        lib.gemm(col, net.w[l.prefix + "w"], out, M=nb * ho * wo, N=l.cout, K=9 * c,
+                 bias=net.w[l.prefix + "b"])
+
+    def _up(self, net: _Net, l: arch.Layer, x, nb, h, w, out):
+        c = l.cin
+        up16 = self.ws.get("up_a16", (nb * 4 * h * w, c), self.op_dtype)
+        lib.gn_apply(x, None, c, 0, nb, h, w, None, None, None, up16, norm=False, silu=False, upsample=2)
+        lib.gemm(up16, net.w[l.prefix + "w"], out, M=nb * 4 * h * w, N=l.cout, K=9 * c,
+                 bias=net.w[l.prefix + "b"], conv=(nb, 2 * h, 2 * w, c, 3))
+
+    def _encoder(self, net: _Net, tag: str, x_in, hint, nb, h, w, keep: bool):
+        """Input blocks + middle. Returns (list of (tensor, c, h, w) per input block, middle)."""
+        ws = self.ws
+        outs = []
+        cur, ch, cw, cc = None, h, w, 0
+        for bi, blk in enumerate(net.plan.input_blocks):
+            for l in blk.layers:
+                if l.kind == "conv_in":
+                    o = ws.get(f"{tag}_hs{bi}", (nb * h * w, l.cout), torch.float32)
+                    c1 = x_in.shape[1]
+                    c2 = hint.shape[1] if hint is not None else 0
+                    lib.conv3x3_small_cin(x_in, hint, c1, c2, nb, h, w, net.w[l.prefix + "w"],
+                                          net.w[l.prefix + "b"], l.cout, o)
+                    cur, cc = o, l.cout
+                elif l.kind == "res":
+                    o = ws.get(f"{tag}_hs{bi}", (nb * ch * cw, l.cout), torch.float32)
+                    self._res(net, tag, l, cur, None, cc, 0, nb, ch, cw, o)
+                    cur, cc = o, l.cout
+                elif l.kind == "attn":
+                    self._attn(net, tag, l, cur, nb, ch, cw)
+                elif l.kind == "down":
+                    o = ws.get(f"{tag}_hs{bi}", (nb * (ch // 2) * (cw // 2), l.cout), torch.float32)
+                    self._down(net, l, cur, nb, ch, cw, o)
+                    cur, cc, ch, cw = o, l.cout, ch // 2, cw // 2
+            outs.append((cur, cc, ch, cw))
+        mid = ws.get(f"{tag}_mid", (nb * ch * cw, cc), torch.float32)
+        m = net.plan.middle.layers
+        self._res(net, tag, m[0], cur, None, cc, 0, nb, ch, cw, mid)
+        self._attn(net, tag, m[1], mid, nb, ch, cw)
+        self._res(net, tag, m[2], mid, None, cc, 0, nb, ch, cw, mid)
+        return outs, (mid, cc, ch, cw)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, c_img: torch.Tensor, control_scales: Sequence[float],
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """eps/v = ControlLDM.forward(x, t, {c_txt, c_img}) for the step loaded with load_step()
+        and the context given to set_context(). x, c_img: fp32 NCHW [nb, 4, h, w] on the device.
+        Returns fp32 NCHW [nb, 4, h, w]."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert c_img.is_cuda and c_img.dtype == torch.float32 and c_img.is_contiguous()
+        nb, _, h, w = x.shape
+        assert nb == self._nb == self.emb_nb, "set_context / set_timesteps batch mismatch"
+        ws, U, Cn = self.ws, self.unet, self.cnet
+        # 1. UNet encoder + middle
+        hs, (mid, mc_, mh, mw) = self._encoder(U, "u", x, None, nb, h, w, True)
+        # 2. ControlNet; zero-convs accumulate into the UNet skips / middle in place
+        chs, (cmid, cmc, cmh, cmw) = self._encoder(Cn, "c", x, c_img, nb, h, w, False)
+        for i, (t, c, th, tw) in enumerate(chs):
+            M = nb * th * tw
+            a16 = ws.get("zc_a16", (M, c), self.op_dtype)
+            lib.gn_apply(t, None, c, 0, nb, th, tw, None, None, None, a16, norm=False, silu=False)
+            tgt = hs[i][0]
+            lib.gemm(a16, Cn.w[f"zero_convs.{i}.w"], tgt, M=M, N=c, K=c, bias=Cn.w[f"zero_convs.{i}.b"],
+                     alpha=float(control_scales[i]), residual=tgt)
+        M = nb * cmh * cmw
+        a16 = ws.get("zc_a16", (M, cmc), self.op_dtype)
+        lib.gn_apply(cmid, None, cmc, 0, nb, cmh, cmw, None, None, None, a16, norm=False, silu=False)
+        lib.gemm(a16, Cn.w["middle_block_out.w"], mid, M=M, N=cmc, K=cmc, bias=Cn.w["middle_block_out.b"],
+                 alpha=float(control_scales[len(chs)]), residual=mid)
+        # 3. UNet decoder over virtual concats
+        cur, cc, ch, cw = mid, mc_, mh, mw
+        stack = list(hs)
+        for bi, blk in enumerate(U.plan.output_blocks):
+            for l in blk.layers:
+                if l.kind == "res":
+                    skip, sc, sh, sw = stack.pop()
+                    assert (sh, sw) == (ch, cw) and cc + sc == l.cin
+                    o = ws.get(f"u_out{bi % 2}", (nb * ch * cw, l.cout), torch.float32)
+                    self._res(U, "u", l, cur, skip, cc, sc, nb, ch, cw, o)
+                    cur, cc = o, l.cout
+                elif l.kind == "attn":
+                    self._attn(U, "u", l, cur, nb, ch, cw)
+                elif l.kind == "up":
+                    o = ws.get(f"u_up{bi % 2}", (nb * 4 * ch * cw, l.cout), torch.float32)
+                    self._up(U, l, cur, nb, ch, cw, o)
+                    cur, cc, ch, cw = o, l.cout, ch * 2, cw * 2
+        # 4. out = conv(silu(gn(h)))  (unet.py:675-679)
+        a16 = ws.get("res_a16", (nb * ch * cw, cc), self.op_dtype)
+        self._gn(cur, None, cc, 0, nb, ch, cw, 1e-5, U.w["out.0.weight"], U.w["out.0.bias"], a16, True)
+        oc = U.cfg["out_channels"]
+        if out is None:
+            out = torch.empty(nb, oc, ch, cw, dtype=torch.float32, device=self.dev)
+        lib.conv3x3_small_cout(a16, nb, ch, cw, cc, U.w["out.2.weight"], U.w["out.2.bias"], oc, out,
+                               nchw=True)
+        return out

@@ -1,0 +1,77 @@
+"""Shared engine plumbing: named workspace buffers and weight packing helpers."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from .. import lib
+
+
+class Workspace:
+    """Named, grow-only device buffers. After one warm-up pass nothing is (re)allocated, which
+    is what CUDA-graph capture needs (the C ABI never allocates)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self.frozen = False
+
+    def get(self, tag: str, shape, dtype, zero: bool = False) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        key = f"{tag}:{dtype}"
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < n:
+            if self.frozen:
+                raise RuntimeError(f"workspace buffer '{tag}' would grow after capture")
+            buf = (torch.zeros if zero else torch.empty)(max(n, 1), dtype=dtype, device=self.device)
+            self._bufs[key] = buf
+        return buf[:n].view(*shape)
+
+    def bytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self._bufs.values())
+
+
+def op16(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=lib.operand_dtype()).contiguous()
+
+
+def f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def pack_conv3x3(w: torch.Tensor, device, cin_pad: int = 0) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] -> op16 [Cout, kh*kw*Cin'] with k = tap*Cin' + c (Cin zero-padded)."""
+    co, ci, kh, kw = w.shape
+    w = w.permute(0, 2, 3, 1)
+    if cin_pad and cin_pad > ci:
+        w = torch.nn.functional.pad(w, (0, cin_pad - ci))
+        ci = cin_pad
+    return op16(w.reshape(co, kh * kw * ci), device)
+
+
+def pack_linear(w: torch.Tensor, device, k_pad: int = 0) -> torch.Tensor:
+    if w.dim() == 4:
+        w = w.reshape(w.shape[0], w.shape[1])
+    if k_pad and k_pad > w.shape[1]:
+        w = torch.nn.functional.pad(w, (0, k_pad - w.shape[1]))
+    return op16(w, device)
+
+
+def geglu_tile(c: int) -> int:
+    """GEMM tile width used for the GEGLU projection of a width-c transformer block."""
+    return 128 if c >= 1280 else (256 if (4 * c) % 128 == 0 else 64)
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor, bn: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Interleave value / gate rows per bn-row tile: tile j = [values j*hb.. | gates j*hb..]."""
+    inner = w.shape[0] // 2
+    hb = bn // 2
+    assert inner % hb == 0
+    wv, wg = w[:inner].view(inner // hb, hb, -1), w[inner:].view(inner // hb, hb, -1)
+    wp = torch.cat([wv, wg], dim=1).reshape(2 * inner, -1)
+    bv, bg = b[:inner].view(inner // hb, hb), b[inner:].view(inner // hb, hb)
+    bp = torch.cat([bv, bg], dim=1).reshape(2 * inner)
+    return op16(wp, device), f32(bp, device)

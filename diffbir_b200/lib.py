@@ -32,6 +32,8 @@ class GemmArgs(C.Structure):
         ("rows_per_vec", C.c_int32), ("out_kind", C.c_int32), ("act", C.c_int32),
         ("geglu", C.c_int32), ("force_bn", C.c_int32),
         ("alpha", C.c_float), ("act_param", C.c_float),
+        ("bias_per_row", C.c_int32), ("reserved0", C.c_int32),
+        ("out2", C.c_void_p), ("ldo2", C.c_int64),
     ]
 
 
@@ -83,7 +85,7 @@ ACT = {None: 0, "none": 0, "gelu": 1, "lrelu": 2, "silu": 3}
 
 def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual=None,
          lda=0, ldb=0, ldo=None, ldr=None, conv=None, act=None, act_param=0.0, alpha=1.0,
-         geglu=False, force_bn=0):
+         geglu=False, force_bn=0, bias_per_row=False, out2=None, ldo2=None):
     """out = residual + alpha * act(A @ B^T + bias + rowvec). conv = (n, h, w, c, ksize)."""
     lib = load()
     g = GemmArgs()
@@ -106,5 +108,138 @@ def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual
     g.alpha = alpha
     g.geglu = 1 if geglu else 0
     g.force_bn = force_bn
+    g.bias_per_row = 1 if bias_per_row else 0
+    g.out2 = _ptr(out2)
+    g.ldo2 = (n_out if ldo2 is None else ldo2)
     check(lib.dbir_gemm(C.byref(g), C.c_void_p(stream_ptr())), "dbir_gemm")
+    count_launch()
+
+
+def _sp():
+    return C.c_void_p(stream_ptr())
+
+
+def _fp(t):
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+def attention(q, k, v, out, *, batch, heads, sq, skv, ldq, ldk, ldv, ldo):
+    """Flash attention, head_dim 64; q/k/v/out are op16 tensors (possibly column slices)."""
+    check(load().dbir_attention(_fp(q), _fp(k), _fp(v), _fp(out), batch, heads, sq, skv,
+                                C.c_int64(ldq), C.c_int64(ldk), C.c_int64(ldv), C.c_int64(ldo),
+                                _sp()), "dbir_attention")
+    count_launch()
+
+
+def gn_workspace_floats(n, hw, c) -> int:
+    lib = load()
+    lib.dbir_gn_workspace_floats.restype = C.c_int64
+    return int(lib.dbir_gn_workspace_floats(n, hw, c))
+
+
+def gn_stats(src1, src2, c1, c2, n, hw, eps, stats, workspace):
+    check(load().dbir_gn_stats(_fp(src1), _fp(src2), c1, c2, n, hw, C.c_float(eps), _fp(stats),
+                               _fp(workspace), _sp()), "dbir_gn_stats")
+    count_launch()
+
+
+def gn_apply(src1, src2, c1, c2, n, h, w, stats, gamma, beta, out, *, norm=True, silu=True,
+             upsample=1, out_raw=None):
+    check(load().dbir_gn_apply(_fp(src1), _fp(src2), c1, c2, n, h, w, _fp(stats), _fp(gamma),
+                               _fp(beta), 1 if norm else 0, 1 if silu else 0, upsample, _fp(out),
+                               _fp(out_raw), _sp()), "dbir_gn_apply")
+    count_launch()
+
+
+def layernorm(x, ldx, rows, c, gamma, beta, out, ldo, eps=1e-5):
+    check(load().dbir_layernorm(_fp(x), C.c_int64(ldx), rows, c, _fp(gamma), _fp(beta),
+                                C.c_float(eps), _fp(out), C.c_int64(ldo),
+                                0 if out.dtype == torch.float32 else 1, _sp()), "dbir_layernorm")
+    count_launch()
+
+
+def swin_window_attention(qkv, ldq, batch, h, w, shift, bias_table, out, ldo):
+    check(load().dbir_swin_window_attention(_fp(qkv), C.c_int64(ldq), batch, h, w, 6, 30, 8, shift,
+                                            _fp(bias_table), _fp(out), C.c_int64(ldo), _sp()),
+          "dbir_swin_window_attention")
+    count_launch()
+
+
+def conv3x3_small_cin(in1, in2, c1, c2, n, h, w, weight_kc, bias, cout, out, in_scale=1.0,
+                      in_shift=0.0):
+    check(load().dbir_conv3x3_small_cin(_fp(in1), _fp(in2), c1, c2, n, h, w, _fp(weight_kc),
+                                        _fp(bias), cout, C.c_float(in_scale), C.c_float(in_shift),
+                                        _fp(out), _sp()), "dbir_conv3x3_small_cin")
+    count_launch()
+
+
+def conv3x3_small_cout(x, n, h, w, cin, weight, bias, cout, out, *, nchw=True, post_scale=1.0,
+                       post_shift=None):
+    check(load().dbir_conv3x3_small_cout(_fp(x), n, h, w, cin, _fp(weight), _fp(bias), cout,
+                                         C.c_float(post_scale), _fp(post_shift), _fp(out),
+                                         1 if nchw else 0, _sp()), "dbir_conv3x3_small_cout")
+    count_launch()
+
+
+def im2col_s2(x, n, h, w, c, pad_lo, out):
+    check(load().dbir_im2col_s2(_fp(x), n, h, w, c, pad_lo, _fp(out), _sp()), "dbir_im2col_s2")
+    count_launch()
+
+
+def linear_f32(x, ldx, m, k, weight, bias, n, y, ldy, silu_in=False, silu_out=False):
+    check(load().dbir_linear_f32(_fp(x), C.c_int64(ldx), m, k, _fp(weight), _fp(bias), n,
+                                 1 if silu_in else 0, 1 if silu_out else 0, _fp(y),
+                                 C.c_int64(ldy), _sp()), "dbir_linear_f32")
+    count_launch()
+
+
+def timestep_embedding(t, m, dim, out):
+    check(load().dbir_timestep_embedding(_fp(t), m, dim, _fp(out), _sp()), "dbir_timestep_embedding")
+    count_launch()
+
+
+def softmax_rows(s, lds, rows, cols, scale, out, ldo):
+    check(load().dbir_softmax_rows(_fp(s), C.c_int64(lds), rows, cols, C.c_float(scale), _fp(out),
+                                   C.c_int64(ldo), _sp()), "dbir_softmax_rows")
+    count_launch()
+
+
+def upsample2x_op16(x, n, h, w, c, out):
+    check(load().dbir_upsample2x_op16(_fp(x), n, h, w, c, _fp(out), _sp()), "dbir_upsample2x_op16")
+    count_launch()
+
+
+def swin_stem(x, n, h, w, r, mean3, rng, cpad, out):
+    arr = (C.c_float * 3)(*mean3)
+    check(load().dbir_swin_stem(_fp(x), n, h, w, r, arr, C.c_float(rng), cpad, _fp(out), _sp()),
+          "dbir_swin_stem")
+    count_launch()
+
+
+def nchw_to_nhwc(x, n, c, hw, out):
+    check(load().dbir_nchw_to_nhwc(_fp(x), n, c, hw, _fp(out), _sp()), "dbir_nchw_to_nhwc")
+    count_launch()
+
+
+def nhwc_to_nchw(x, n, c, hw, out):
+    check(load().dbir_nhwc_to_nchw(_fp(x), n, c, hw, _fp(out), _sp()), "dbir_nhwc_to_nchw")
+    count_launch()
+
+
+def sampler_step(eps_c, eps_u, cfg, x, noise, coef, mode, numel, x_out):
+    check(load().dbir_sampler_step(_fp(eps_c), _fp(eps_u), C.c_float(cfg), _fp(x), _fp(noise),
+                                   _fp(coef), mode, C.c_int64(numel), _fp(x_out), _sp()),
+          "dbir_sampler_step")
+    count_launch()
+
+
+def tile_gather(full, b, c, h, w, coords, ntiles, tile, tiles):
+    check(load().dbir_tile_gather(_fp(full), b, c, h, w, _fp(coords), ntiles, tile, _fp(tiles),
+                                  _sp()), "dbir_tile_gather")
+    count_launch()
+
+
+def tile_blend(tiles, b, c, h, w, coords, ntiles, tile, weights, out):
+    check(load().dbir_tile_blend(_fp(tiles), b, c, h, w, _fp(coords), ntiles, tile, _fp(weights),
+                                 _fp(out), _sp()), "dbir_tile_blend")
     count_launch()

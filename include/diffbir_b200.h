@@ -53,8 +53,104 @@ typedef struct dbir_gemm_args {
   int32_t force_bn;     /* 0 = auto tile width, else 32/64/128/160/256 (required with geglu) */
   float alpha;          /* scale applied before the residual add (control strength) */
   float act_param;
+  int32_t bias_per_row; /* 1: bias[row] instead of bias[col] (transposed products) */
+  int32_t reserved0;
+  void* out2;           /* optional op16 copy of the result [rows, ldo2] (operand of the next op) */
+  int64_t ldo2;
 } dbir_gemm_args;
 int dbir_gemm(const dbir_gemm_args* args, void* stream);
+
+/* ---- flash attention, head_dim 64 (tcgen05) ------------------------------------------
+ * out[b, i, h*64 + :] = softmax_j(q_h[i] . k_h[j] / 8) v_h[j]; q/k/v/out are op16 matrices
+ * [batch, s, ld*] whose first heads*64 columns (from the given base pointer) hold the heads.
+ * Replaces F.scaled_dot_product_attention and the head split/merge copies in
+ * SDPCrossAttention.forward (attention.py:189-216); kv = text context for attn2.
+ */
+int dbir_attention(const void* q, const void* k, const void* v, void* out, int32_t batch,
+                   int32_t heads, int32_t sq, int32_t skv, int64_t ldq, int64_t ldk, int64_t ldv,
+                   int64_t ldo, void* stream);
+
+/* ---- GroupNorm (32 groups) / LayerNorm ------------------------------------------------
+ * dbir_gn_stats: per-(image, group) mean and rstd of the virtual concat [src1 | src2] (fp32
+ * NHWC, c2 may be 0) -> stats[n][32][2]. workspace: dbir_gn_workspace_floats() floats,
+ * zero-initialised once by the caller. Replaces the statistics half of GroupNorm32
+ * (util.py:191-193, eps 1e-5) / Normalize (attention.py:48-51, vae.py:18-21, eps 1e-6) and
+ * the torch.cat before output-block ResBlocks (controlnet.py:39-44).
+ * dbir_gn_apply: out = silu?(gn(x)) as op16 NHWC, optionally 2x nearest-upsampled
+ * (unet.py:76-78, vae.py:37-40); do_norm = 0 gives a plain cast (operand of Down/Upsample
+ * convs, 1x1 skip convs); out_raw (optional) receives the un-normalised cast.
+ * dbir_layernorm: op16 out[rows, ldo] = LN(x[rows, c]) (attention.py:257-259,
+ * swinir.py:208,214,722,783; eps 1e-5); columns [c, ldo) are zero-filled.
+ */
+int64_t dbir_gn_workspace_floats(int32_t n, int32_t hw, int32_t c);
+int dbir_gn_stats(const float* src1, const float* src2, int32_t c1, int32_t c2, int32_t n,
+                  int32_t hw, float eps, float* stats, float* workspace, void* stream);
+int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, int32_t c2, int32_t n,
+                  int32_t h, int32_t w, const float* stats, const float* gamma,
+                  const float* beta, int32_t do_norm, int32_t do_silu, int32_t upsample,
+                  void* out, void* out_raw, void* stream);
+int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t c, const float* gamma,
+                   const float* beta, float eps, void* out, int64_t ldo, int32_t out_kind,
+                   void* stream);   /* out_kind 0 = fp32, 1 = op16 */
+
+/* ---- SwinIR window attention -----------------------------------------------------------
+ * One 8x8 window per CTA; qkv op16 [batch*h*w, ldq] with columns [q | k | v] x (heads, dim)
+ * as produced by WindowAttention.qkv (swinir.py:104,122-123); out op16 [batch*h*w, ldo]
+ * (first heads*dim columns) in original token order. shift = 0 (W-MSA) or 4 (SW-MSA):
+ * replaces torch.roll + window_partition + q k^T + bias + mask + softmax + @v +
+ * window_reverse + roll (swinir.py:120-151, 255-276).
+ */
+int dbir_swin_window_attention(const void* qkv, int64_t ldq, int32_t batch, int32_t h, int32_t w,
+                               int32_t heads, int32_t head_dim, int32_t window, int32_t shift,
+                               const float* bias_table, void* out, int64_t ldo, void* stream);
+
+/* ---- small / memory-bound ops ------------------------------------------------------------
+ * conv3x3_small_cin : stems with <= 16 input channels; input = virtual concat of two NCHW
+ *   fp32 tensors scaled by in_scale/in_shift; weight fp32 [9*Cin, Cout]; out NHWC fp32
+ *   (unet.py:500-506, controlnet.py:158-166,316; vae.py:322-324,482-484).
+ * conv3x3_small_cout: heads with 3/4/8 output channels; op16 NHWC in, weight fp32
+ *   [Cout, 9*Cin], out = (conv + bias) * post_scale + post_shift[c], NCHW or NHWC fp32
+ *   (unet.py:675-679 out conv; vae.py:340-345,520-522; swinir.py:811,885-887).
+ * im2col_s2: 3x3 stride-2 patches of fp32 NHWC -> op16 [n*ho*wo, 9c] for dbir_gemm
+ *   (Downsample unet.py:99 pad_lo=1; vae.py:51-55 pad_lo=0).
+ * linear_f32: y = act_out(act_in(x) W^T + b), small row counts, all fp32
+ *   (time_embed / emb_layers unet.py:166-172,494-498,616-617; quant convs vae.py:569-570).
+ * timestep_embedding: util.py:128-148. softmax_rows: vae.py:232-282 (mid attention).
+ * sampler_step: CFG mix + x0 + posterior / DDIM update, one launch per step
+ *   (spaced_sampler.py:118-184, ddim_sampler.py:98-146); coef -> 8 floats of the step.
+ * tile_gather / tile_blend: mixture-of-diffusers tiling (utils/common.py:123-232).
+ */
+int dbir_conv3x3_small_cin(const float* in1, const float* in2, int32_t c1, int32_t c2, int32_t n,
+                           int32_t h, int32_t w, const float* weight_kc, const float* bias,
+                           int32_t cout, float in_scale, float in_shift, float* out_nhwc,
+                           void* stream);
+int dbir_conv3x3_small_cout(const void* in_nhwc, int32_t n, int32_t h, int32_t w, int32_t cin,
+                            const float* weight, const float* bias, int32_t cout,
+                            float post_scale, const float* post_shift, float* out,
+                            int32_t out_nchw, void* stream);
+int dbir_im2col_s2(const float* in_nhwc, int32_t n, int32_t h, int32_t w, int32_t c,
+                   int32_t pad_lo, void* out, void* stream);
+int dbir_linear_f32(const float* x, int64_t ldx, int32_t m, int32_t k, const float* weight,
+                    const float* bias, int32_t n, int32_t silu_in, int32_t silu_out, float* y,
+                    int64_t ldy, void* stream);
+int dbir_timestep_embedding(const float* t, int32_t m, int32_t dim, float* out, void* stream);
+int dbir_softmax_rows(const float* s, int64_t lds, int32_t rows, int32_t cols, float scale,
+                      void* out, int64_t ldo, void* stream);
+int dbir_upsample2x_op16(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out,
+                         void* stream);
+int dbir_swin_stem(const float* in_nchw, int32_t n, int32_t h, int32_t w, int32_t r,
+                   const float* mean3, float range, int32_t cpad, void* out, void* stream);
+int dbir_nchw_to_nhwc(const float* in, int32_t n, int32_t c, int32_t hw, float* out, void* stream);
+int dbir_nhwc_to_nchw(const float* in, int32_t n, int32_t c, int32_t hw, float* out, void* stream);
+int dbir_sampler_step(const float* eps_cond, const float* eps_uncond, float cfg_scale,
+                      const float* x, const float* noise, const float* coef, int32_t mode,
+                      int64_t numel, float* x_out, void* stream);
+int dbir_tile_gather(const float* full, int32_t b, int32_t c, int32_t h, int32_t w,
+                     const int32_t* coords, int32_t ntiles, int32_t tile, float* tiles,
+                     void* stream);
+int dbir_tile_blend(const float* tiles, int32_t b, int32_t c, int32_t h, int32_t w,
+                    const int32_t* coords, int32_t ntiles, int32_t tile, const float* weights,
+                    float* out, void* stream);
 
 #ifdef __cplusplus
 }
