@@ -178,8 +178,9 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int m, in
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m * half) return;
   const int r = i / half, j = i % half;
-  const float f = expf(-9.210340371976184f * static_cast<float>(j) / static_cast<float>(half));
-  const float a = t[r] * f;
+  // frequency correctly rounded to fp32 (the reference holds fp32 freqs), argument in fp32
+  const float f = static_cast<float>(exp(-9.210340371976184 * static_cast<double>(j) / static_cast<double>(half)));
+  const float a = __fmul_rn(t[r], f);
   out[static_cast<long long>(r) * dim + j] = cosf(a);
   out[static_cast<long long>(r) * dim + half + j] = sinf(a);
 }

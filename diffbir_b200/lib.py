@@ -59,6 +59,40 @@ def check(rc: int, what: str = ""):
         raise DbirError(f"{what} failed (rc={rc}): {msg}")
 
 
+_profile = None   # list of (kind, flops, start_event, end_event) while profiling
+
+
+def profile_begin():
+    """bench.py's kernel census: brackets every GEMM / attention launch with CUDA events."""
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    global _profile
+    torch.cuda.synchronize()
+    out = [(k, info, fl, e0.elapsed_time(e1)) for k, info, fl, e0, e1 in _profile]
+    _profile = None
+    return out
+
+
+class _Prof:
+    def __init__(self, kind, info, flops):
+        self.kind, self.info, self.flops = kind, info, flops
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _profile is not None:
+            self.e1.record()
+            _profile.append((self.kind, self.info, self.flops, self.e0, self.e1))
+
+
 def count_launch(n: int = 1):
     global _launches
     _launches += n
@@ -111,7 +145,8 @@ def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual
     g.bias_per_row = 1 if bias_per_row else 0
     g.out2 = _ptr(out2)
     g.ldo2 = (n_out if ldo2 is None else ldo2)
-    check(lib.dbir_gemm(C.byref(g), C.c_void_p(stream_ptr())), "dbir_gemm")
+    with _Prof("conv" if conv is not None else "gemm", (M, N, K), 2.0 * M * N * K):
+        check(lib.dbir_gemm(C.byref(g), C.c_void_p(stream_ptr())), "dbir_gemm")
     count_launch()
 
 
@@ -125,9 +160,10 @@ def _fp(t):
 
 def attention(q, k, v, out, *, batch, heads, sq, skv, ldq, ldk, ldv, ldo):
     """Flash attention, head_dim 64; q/k/v/out are op16 tensors (possibly column slices)."""
-    check(load().dbir_attention(_fp(q), _fp(k), _fp(v), _fp(out), batch, heads, sq, skv,
-                                C.c_int64(ldq), C.c_int64(ldk), C.c_int64(ldv), C.c_int64(ldo),
-                                _sp()), "dbir_attention")
+    with _Prof("attention", (batch, heads, sq, skv), 4.0 * batch * heads * sq * skv * 64):
+        check(load().dbir_attention(_fp(q), _fp(k), _fp(v), _fp(out), batch, heads, sq, skv,
+                                    C.c_int64(ldq), C.c_int64(ldk), C.c_int64(ldv), C.c_int64(ldo),
+                                    _sp()), "dbir_attention")
     count_launch()
 
 

@@ -1,0 +1,5 @@
+from .cldm import ControlLDM
+from .gaussian_diffusion import Diffusion
+from .swinir import SwinIR
+
+__all__ = ["ControlLDM", "Diffusion", "SwinIR"]

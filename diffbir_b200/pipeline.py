@@ -1,0 +1,169 @@
+"""Pipeline / SwinIRPipeline — drop-in counterparts of the reference's diffbir.pipeline
+(pipeline.py:43-321, 369-397): same constructor, same 26-argument `run`, uint8 NHWC in/out.
+The orchestration (resize, pads, crops, colour fix, quantisation) is the reference's, the
+networks are the kernel engines behind diffbir_b200.model.{SwinIR, ControlLDM}.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .model import ControlLDM, Diffusion
+from .sampler import DDIMSampler, SpacedSampler
+from .utils.common import wavelet_reconstruction
+
+
+def resize_short_edge_to(imgs: torch.Tensor, size: int) -> torch.Tensor:
+    _, _, h, w = imgs.size()
+    if h == w:
+        out_h, out_w = size, size
+    elif h < w:
+        out_h, out_w = size, int(w * (size / h))
+    else:
+        out_h, out_w = int(h * (size / w)), size
+    return F.interpolate(imgs, size=(out_h, out_w), mode="bicubic", antialias=True)
+
+
+def pad_to_multiples_of(imgs: torch.Tensor, multiple: int) -> torch.Tensor:
+    _, _, h, w = imgs.size()
+    if h % multiple == 0 and w % multiple == 0:
+        return imgs.clone()
+    ph, pw = map(lambda x: (x + multiple - 1) // multiple * multiple - x, (h, w))
+    return F.pad(imgs, pad=(0, pw, 0, ph), mode="constant", value=0)
+
+
+class Pipeline:
+    def __init__(self, cleaner, cldm: ControlLDM, diffusion: Diffusion, cond_fn, device: str) -> None:
+        self.cleaner = cleaner
+        self.cldm = cldm
+        self.diffusion = diffusion
+        self.cond_fn = cond_fn          # restoration guidance: dead code in the reference
+        self.device = device
+        self.output_size: Tuple[int, int] = None
+        self.taps: Optional[dict] = None   # set to {} to capture intermediates (tests)
+
+    def set_output_size(self, lq_size: Tuple[int]) -> None:
+        h, w = lq_size[2:]
+        self.output_size = (h, w)
+
+    def apply_cleaner(self, lq, tiled, tile_size, tile_stride):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def apply_cldm(self, cond_img, steps, strength, vae_encoder_tiled, vae_encoder_tile_size,
+                   vae_decoder_tiled, vae_decoder_tile_size, cldm_tiled, cldm_tile_size,
+                   cldm_tile_stride, pos_prompt, neg_prompt, cfg_scale, start_point_type,
+                   sampler_type, noise_aug, rescale_cfg, s_churn, s_tmin, s_tmax, s_noise, eta,
+                   order, x_T: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pipeline.py:71-233."""
+        if vae_encoder_tiled or vae_decoder_tiled:
+            raise NotImplementedError("tiled VAE is outside the B200 hot path (180 GB HBM per GPU)")
+        bs, _, h0, w0 = cond_img.shape
+        cond_img = pad_to_multiples_of(cond_img, multiple=8 if cldm_tiled else 64)
+        # The reference encodes the (identical) condition image twice (pipeline.py:117-128);
+        # the latent is deterministic (posterior mode), so it is encoded once and shared.
+        cond = self.cldm.prepare_condition(cond_img, [pos_prompt] * bs)
+        uncond = dict(c_txt=self.cldm.clip(self.cldm.tokenize([neg_prompt] * bs)), c_img=cond["c_img"].clone())
+        h1, w1 = cond["c_img"].shape[2:]
+        if cldm_tiled and (h1 < cldm_tile_size // 8 or w1 < cldm_tile_size // 8):
+            print("[Diffusion]: the input size is tiny and unnecessary to tile.")
+            cldm_tiled = False
+        if not cldm_tiled:
+            cond["c_img"] = pad_to_multiples_of(cond["c_img"], multiple=8)
+            uncond["c_img"] = pad_to_multiples_of(uncond["c_img"], multiple=8)
+        elif cldm_tile_size % 64 != 0:
+            raise ValueError("Diffusion tile size must be a multiple of 64")
+        h2, w2 = cond["c_img"].shape[2:]
+        if x_T is None:
+            if start_point_type == "cond":
+                x_T = self.diffusion.q_sample(
+                    cond["c_img"],
+                    torch.full((bs,), self.diffusion.num_timesteps - 1, dtype=torch.long, device=self.device),
+                    torch.randn(cond["c_img"].shape, dtype=torch.float32, device=self.device))
+            else:
+                x_T = torch.randn((bs, 4, h2, w2), dtype=torch.float32, device=self.device)
+        if noise_aug > 0:
+            cond["c_img"] = self.diffusion.q_sample(
+                x_start=cond["c_img"], t=torch.full(size=(bs,), fill_value=noise_aug, device=self.device),
+                noise=torch.randn_like(cond["c_img"]))
+            uncond["c_img"] = cond["c_img"].detach().clone()
+        control_scales = self.cldm.control_scales
+        self.cldm.control_scales = [strength] * 13
+        betas, parameterization = self.diffusion.betas, self.diffusion.parameterization
+        if sampler_type == "spaced":
+            sampler = SpacedSampler(betas, parameterization, rescale_cfg)
+        elif sampler_type == "ddim":
+            sampler = DDIMSampler(betas, parameterization, rescale_cfg, eta=0)
+        else:
+            raise NotImplementedError(f"{sampler_type}: only the spaced and DDIM samplers are on the B200 hot path")
+        z = sampler.sample(model=self.cldm, device=self.device, steps=steps, x_size=(bs, 4, h2, w2),
+                           cond=cond, uncond=uncond, cfg_scale=cfg_scale, tiled=cldm_tiled,
+                           tile_size=cldm_tile_size // 8, tile_stride=cldm_tile_stride // 8, x_T=x_T,
+                           progress=True)
+        z = z[..., :h1, :w1].contiguous()
+        x = self.cldm.vae_decode(z)
+        x = x[:, :, :h0, :w0]
+        self.cldm.control_scales = control_scales
+        if self.taps is not None:
+            self.taps.update(z=z, decoded=x, cond=cond, uncond=uncond)
+        return x
+
+    @torch.no_grad()
+    def run(self, lq: np.ndarray, steps: int, strength: float, cleaner_tiled: bool,
+            cleaner_tile_size: int, cleaner_tile_stride: int, vae_encoder_tiled: bool,
+            vae_encoder_tile_size: int, vae_decoder_tiled: bool, vae_decoder_tile_size: int,
+            cldm_tiled: bool, cldm_tile_size: int, cldm_tile_stride: int, pos_prompt: str,
+            neg_prompt: str, cfg_scale: float, start_point_type: str, sampler_type: str,
+            noise_aug: int, rescale_cfg: bool, s_churn: float, s_tmin: float, s_tmax: float,
+            s_noise: float, eta: float, order: int, x_T: Optional[torch.Tensor] = None) -> np.ndarray:
+        """pipeline.py:235-321: uint8 [B,H,W,3] (numpy or pinned CPU tensor) -> uint8 numpy."""
+        host = torch.from_numpy(lq) if isinstance(lq, np.ndarray) else lq
+        lq_dev = host.to(self.device, non_blocking=True)                        # H2D
+        out = self.run_device(lq_dev, steps, strength, cleaner_tiled, cleaner_tile_size,
+                              cleaner_tile_stride, vae_encoder_tiled, vae_encoder_tile_size,
+                              vae_decoder_tiled, vae_decoder_tile_size, cldm_tiled, cldm_tile_size,
+                              cldm_tile_stride, pos_prompt, neg_prompt, cfg_scale, start_point_type,
+                              sampler_type, noise_aug, rescale_cfg, s_churn, s_tmin, s_tmax, s_noise,
+                              eta, order, x_T=x_T)
+        return out.cpu().numpy()                                                # D2H
+
+    @torch.no_grad()
+    def run_device(self, lq_dev: torch.Tensor, steps, strength, cleaner_tiled, cleaner_tile_size,
+                   cleaner_tile_stride, vae_encoder_tiled, vae_encoder_tile_size, vae_decoder_tiled,
+                   vae_decoder_tile_size, cldm_tiled, cldm_tile_size, cldm_tile_stride, pos_prompt,
+                   neg_prompt, cfg_scale, start_point_type, sampler_type, noise_aug, rescale_cfg,
+                   s_churn, s_tmin, s_tmax, s_noise, eta, order, x_T=None) -> torch.Tensor:
+        """Same as run() with the uint8 NHWC input and output resident on the device."""
+        lq_tensor = lq_dev.to(torch.float32).div(255).clamp(0, 1).permute(0, 3, 1, 2).contiguous()
+        self.set_output_size(lq_tensor.size())
+        cond_img = self.apply_cleaner(lq_tensor, cleaner_tiled, cleaner_tile_size, cleaner_tile_stride)
+        assert all(x >= 512 for x in cond_img.shape[2:]), (
+            "The resolution of stage-1 model output should be greater than 512, "
+            "since it will be used as condition for stage-2 model.")
+        if self.taps is not None:
+            self.taps["clean"] = cond_img
+        sample = self.apply_cldm(cond_img, steps, strength, vae_encoder_tiled, vae_encoder_tile_size,
+                                 vae_decoder_tiled, vae_decoder_tile_size, cldm_tiled, cldm_tile_size,
+                                 cldm_tile_stride, pos_prompt, neg_prompt, cfg_scale, start_point_type,
+                                 sampler_type, noise_aug, rescale_cfg, s_churn, s_tmin, s_tmax, s_noise,
+                                 eta, order, x_T=x_T)
+        sample = F.interpolate(wavelet_reconstruction((sample + 1) / 2, cond_img), size=self.output_size,
+                               mode="bicubic", antialias=True)
+        return (sample * 255.0).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
+class SwinIRPipeline(Pipeline):
+    def apply_cleaner(self, lq: torch.Tensor, tiled: bool, tile_size: int, tile_stride: int) -> torch.Tensor:
+        """pipeline.py:371-397 (un-tiled branch; 180 GB of HBM make cleaner tiling unnecessary)."""
+        if tiled and (lq.size(2) < tile_size or lq.size(3) < tile_size):
+            tiled = False
+        if tiled:
+            raise NotImplementedError("tiled stage-1 cleaner is outside the B200 hot path")
+        if min(lq.shape[2:]) < 512:
+            lq = resize_short_edge_to(lq, size=512)
+        h0, w0 = lq.shape[2:]
+        lq = pad_to_multiples_of(lq, multiple=64)
+        return self.cleaner(lq)[:, :, :h0, :w0]

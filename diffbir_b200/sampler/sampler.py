@@ -1,0 +1,278 @@
+"""Spaced (DDPM-respaced) and DDIM samplers — counterparts of the reference's
+diffbir.sampler.{SpacedSampler, DDIMSampler} (sampler/sampler.py, spaced_sampler.py,
+ddim_sampler.py) with the same constructors and `sample(...)` signature.
+
+When `model` is a diffbir_b200 ControlLDM the loop runs on the kernel engine:
+  * cond and uncond branches (and, when tiled, all latent tiles) are ONE batched forward,
+    captured once in a CUDA graph and replayed every step;
+  * text K/V and every time embedding are computed before the loop;
+  * CFG mix + x0 + posterior/DDIM update is one fused kernel per step (dbir_sampler_step);
+  * tiles are gathered / Gaussian-blended on the device in the reference's accumulation order;
+    with torch.distributed initialised the tiles are sharded round-robin over the ranks and
+    re-assembled by a single all-gather per step (every rank then blends and updates the same
+    full latent with the same RNG stream).
+Noise is drawn with torch.randn_like once per step exactly like the reference
+(spaced_sampler.py:181, ddim_sampler.py:143), so seeds reproduce.
+Any other callable `model(x, t, cond)` takes a plain PyTorch loop with identical arithmetic.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import lib
+from ..utils.common import gaussian_weights, sliding_windows
+
+
+def space_timesteps(num_timesteps: int, steps: int) -> np.ndarray:
+    """space_timesteps(num_timesteps, str(steps)) — spaced_sampler.py:14-64 (single section)."""
+    stride = 1.0 if steps <= 1 else (num_timesteps - 1) / (steps - 1)
+    out, cur = [], 0.0
+    for _ in range(steps):
+        out.append(round(cur))
+        cur += stride
+    return np.array(sorted(set(out)), dtype=np.int32)
+
+
+class Sampler:
+    def __init__(self, betas: np.ndarray, parameterization: str, rescale_cfg: bool):
+        self.num_timesteps = len(betas)
+        self.training_betas = betas
+        self.training_alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+        self.parameterization = parameterization
+        self.rescale_cfg = rescale_cfg
+
+    def get_cfg_scale(self, default_cfg_scale: float, model_t: int) -> float:
+        """Cosine CFG ramp — sampler/sampler.py:31-38."""
+        if self.rescale_cfg and default_cfg_scale > 1:
+            return 1 + default_cfg_scale * ((1 - math.cos(math.pi * ((1000 - model_t) / 1000) ** 5.0)) / 2)
+        return default_cfg_scale
+
+    # ---- subclass interface -------------------------------------------------------------
+    def make_schedule(self, steps: int):
+        raise NotImplementedError
+
+    def _step_coefs(self) -> Tuple[np.ndarray, torch.Tensor, int]:
+        """(model timesteps ascending, fp32 coefficient rows [S, 8] per table index, kernel mode)"""
+        raise NotImplementedError
+
+    # ---- shared driver --------------------------------------------------------------------
+    @torch.no_grad()
+    def sample(self, model, device, steps: int, x_size: Tuple[int], cond: Dict[str, torch.Tensor],
+               uncond: Optional[Dict[str, torch.Tensor]], cfg_scale: float, tiled: bool = False,
+               tile_size: int = -1, tile_stride: int = -1, x_T: Optional[torch.Tensor] = None,
+               progress: bool = True) -> torch.Tensor:
+        self.make_schedule(steps)
+        ts, coefs, mode = self._step_coefs()
+        if x_T is None:
+            x_T = torch.randn(x_size, device=device, dtype=torch.float32)
+        from ..model.cldm import ControlLDM
+        if isinstance(model, ControlLDM):
+            return self._sample_engine(model, ts, coefs, mode, x_T, cond, uncond, cfg_scale, tiled,
+                                       tile_size, tile_stride)
+        return self._sample_generic(model, ts, coefs, mode, x_T, cond, uncond, cfg_scale, tiled,
+                                    tile_size, tile_stride)
+
+    # ---- kernel-engine path -----------------------------------------------------------------
+    def _sample_engine(self, model, ts, coefs, mode, x_T, cond, uncond, cfg_scale, tiled, tile_size,
+                       tile_stride):
+        model._build()
+        eng = model.engine
+        dev = eng.dev
+        x = x_T.to(dev, torch.float32).contiguous().clone()
+        B, C, H, W = x.shape
+        use_cfg = not (uncond is None or cfg_scale == 1.0)
+        conds = [cond, uncond] if use_cfg else [cond]
+        nbr = len(conds)
+        coefs = coefs.to(dev)
+        order = list(range(len(ts)))[::-1]                     # table index of each loop iteration
+        model_ts = [int(ts[i]) for i in order]
+
+        import torch.distributed as dist
+        world, rank = (dist.get_world_size(), dist.get_rank()) if (tiled and dist.is_available() and dist.is_initialized()) else (1, 0)
+
+        if tiled:
+            wins = sliding_windows(H, W, tile_size, tile_stride)
+            T = len(wins)
+            all_coords = torch.tensor([[a, c] for a, _, c, _ in wins], dtype=torch.int32, device=dev)
+            mine = list(range(rank, T, world))                 # round-robin tile ownership
+            slots = (T + world - 1) // world
+            my_coords = all_coords[mine].contiguous()
+            Tl, ts_ = len(mine), tile_size
+            wts = torch.tensor(gaussian_weights(ts_, ts_), dtype=torch.float32, device=dev)
+            nb = nbr * Tl * B
+            c_img = torch.empty(nbr, Tl * B, C, ts_, ts_, device=dev)
+            for j, cd in enumerate(conds):
+                lib.tile_gather(cd["c_img"].to(dev, torch.float32).contiguous(), B, C, H, W, my_coords,
+                                Tl, ts_, c_img[j])
+            c_img = c_img.view(nb, C, ts_, ts_)
+            ctx = torch.cat([cd["c_txt"].to(dev, torch.float32).repeat(Tl, 1, 1) for cd in conds], 0)
+            x_in = torch.empty(nb, C, ts_, ts_, device=dev)
+            send = torch.zeros(nbr, slots, B, C, ts_, ts_, device=dev)
+            recv = torch.empty(world, nbr, slots, B, C, ts_, ts_, device=dev) if world > 1 else None
+            eps_full = torch.empty(nbr, B, C, H, W, device=dev)
+        else:
+            nb = nbr * B
+            c_img = torch.cat([cd["c_img"].to(dev, torch.float32) for cd in conds], 0).contiguous()
+            ctx = torch.cat([cd["c_txt"].to(dev, torch.float32) for cd in conds], 0)
+            x_in = torch.empty(nb, C, H, W, device=dev)
+        eps = torch.empty_like(x_in)
+
+        scales = [float(s) for s in model.control_scales]
+        eng.set_context(ctx)
+        eng.set_timesteps(model_ts, nb)
+        model._ctx_key = model._t_key = None                    # generic-path caches are now stale
+
+        def fill_inputs():
+            if tiled:
+                v = x_in.view(nbr, Tl * B, C, ts_, ts_)
+                lib.tile_gather(x, B, C, H, W, my_coords, Tl, ts_, v[0])
+                for j in range(1, nbr):
+                    v[j].copy_(v[0])
+            else:
+                v = x_in.view(nbr, B, C, H, W)
+                for j in range(nbr):
+                    v[j].copy_(x)
+
+        # warm-up (sizes every workspace buffer), then capture the forward once
+        eng.load_step(0)
+        fill_inputs()
+        eng.forward(x_in, c_img, scales, out=eps)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib.launches()
+        with torch.cuda.graph(graph):
+            eng.forward(x_in, c_img, scales, out=eps)
+        graph_launches = lib.launches() - n0          # kernels per replay
+        lib.count_launch(-graph_launches)             # capture itself executes nothing
+
+        x_next = torch.empty_like(x)
+        for it, tab_idx in enumerate(order):
+            eng.load_step(it)
+            fill_inputs()
+            graph.replay()
+            lib.count_launch(graph_launches)
+            if tiled:
+                ev = eps.view(nbr, Tl, B, C, ts_, ts_)
+                if world > 1:
+                    send[:, :Tl].copy_(ev)
+                    dist.all_gather_into_tensor(recv, send)
+                    # [world, nbr, slots, ...] -> [nbr, slots, world, ...]: tile t = slot*world + rank
+                    tiles = recv.permute(1, 2, 0, 3, 4, 5, 6).reshape(nbr, slots * world, B, C, ts_, ts_).contiguous()
+                else:
+                    tiles = ev
+                for j in range(nbr):
+                    lib.tile_blend(tiles[j], B, C, H, W, all_coords, T, ts_, wts, eps_full[j])
+                e_c, e_u = eps_full[0], (eps_full[1] if use_cfg else None)
+            else:
+                ev = eps.view(nbr, B, C, H, W)
+                e_c, e_u = ev[0], (ev[1] if use_cfg else None)
+            noise = torch.randn_like(x)
+            cur_cfg = self.get_cfg_scale(cfg_scale, model_ts[it])
+            lib.sampler_step(e_c, e_u, cur_cfg, x, noise, coefs[tab_idx], mode, x.numel(), x_next)
+            x, x_next = x_next, x
+        return x
+
+    # ---- plain PyTorch path for foreign models --------------------------------------------
+    def _sample_generic(self, model, ts, coefs, mode, x_T, cond, uncond, cfg_scale, tiled, tile_size,
+                        tile_stride):
+        x = x_T
+        dev = x.device
+        coefs = coefs.to(dev)
+        fwd = model
+        if tiled:
+            def fwd(xx, tt, cd):
+                out = torch.zeros_like(xx)
+                cnt = torch.zeros_like(xx)
+                w = torch.tensor(gaussian_weights(tile_size, tile_size)[None, None], dtype=xx.dtype, device=dev)
+                for a, b, c, d in sliding_windows(xx.shape[2], xx.shape[3], tile_size, tile_stride):
+                    out[..., a:b, c:d] += model(xx[..., a:b, c:d], tt, {"c_txt": cd["c_txt"], "c_img": cd["c_img"][..., a:b, c:d]}) * w
+                    cnt[..., a:b, c:d] += w
+                return out / cnt
+        for tab_idx in list(range(len(ts)))[::-1]:
+            step = int(ts[tab_idx])
+            model_t = torch.full((x.shape[0],), step, device=dev, dtype=torch.long)
+            s = self.get_cfg_scale(cfg_scale, step)
+            if uncond is None or s == 1.0:
+                e = fwd(x, model_t, cond)
+            else:
+                ec, eu = fwd(x, model_t, cond), fwd(x, model_t, uncond)
+                e = eu + s * (ec - eu)
+            c = coefs[tab_idx]
+            noise = torch.randn_like(x)
+            if mode in (0, 1):
+                x0 = c[0] * x - c[1] * e
+                x = (c[2] * x0 + c[3] * x) + c[4] * noise
+            else:
+                if mode == 3:
+                    e = c[5] * e + c[1] * x
+                x0 = (x - c[1] * e) / c[0]
+                x = c[2] * x0 + c[3] * e + c[4] * noise
+        return x
+
+
+class SpacedSampler(Sampler):
+    def make_schedule(self, num_steps: int) -> None:
+        """spaced_sampler.py:77-116 — respaced betas and posterior tables in fp64."""
+        used = space_timesteps(self.num_timesteps, num_steps)
+        betas, last = [], 1.0
+        for i in used:
+            betas.append(1 - self.training_alphas_cumprod[i] / last)
+            last = self.training_alphas_cumprod[i]
+        self.timesteps = used
+        b = np.array(betas, dtype=np.float64)
+        a = 1.0 - b
+        ac = np.cumprod(a, axis=0)
+        ac_prev = np.append(1.0, ac[:-1])
+        with np.errstate(divide="ignore"):
+            self.tables = dict(
+                sqrt_alphas_cumprod=np.sqrt(ac), sqrt_one_minus_alphas_cumprod=np.sqrt(1 - ac),
+                sqrt_recip_alphas_cumprod=np.sqrt(1.0 / ac), sqrt_recipm1_alphas_cumprod=np.sqrt(1.0 / ac - 1),
+                posterior_variance=b * (1.0 - ac_prev) / (1.0 - ac),
+                posterior_mean_coef1=b * np.sqrt(ac_prev) / (1.0 - ac),
+                posterior_mean_coef2=(1.0 - ac_prev) * np.sqrt(a) / (1.0 - ac))
+
+    def _step_coefs(self):
+        tb = {k: torch.tensor(v, dtype=torch.float32) for k, v in self.tables.items()}
+        S = len(self.timesteps)
+        c = torch.zeros(S, 8, dtype=torch.float32)
+        if self.parameterization == "eps":
+            c[:, 0], c[:, 1], mode = tb["sqrt_recip_alphas_cumprod"], tb["sqrt_recipm1_alphas_cumprod"], 0
+        else:
+            c[:, 0], c[:, 1], mode = tb["sqrt_alphas_cumprod"], tb["sqrt_one_minus_alphas_cumprod"], 1
+        c[:, 2], c[:, 3] = tb["posterior_mean_coef1"], tb["posterior_mean_coef2"]
+        nonzero = (torch.arange(S) != 0).float()                  # spaced_sampler.py:182
+        c[:, 4] = nonzero * torch.sqrt(tb["posterior_variance"])
+        return self.timesteps, c, mode
+
+
+class DDIMSampler(Sampler):
+    def __init__(self, betas, parameterization, rescale_cfg, eta: float):
+        super().__init__(betas, parameterization, rescale_cfg)
+        self.eta = eta
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform"):
+        """ddim_sampler.py:13-58, 73-96 (uniform stride, +1 offset)."""
+        c = self.num_timesteps // ddim_num_steps
+        self.ddim_timesteps = np.asarray(list(range(0, self.num_timesteps, c))) + 1
+        ac = self.training_alphas_cumprod
+        alphas = ac[self.ddim_timesteps]
+        alphas_prev = np.asarray([ac[0]] + ac[self.ddim_timesteps[:-1]].tolist())
+        sigmas = self.eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+        self.tables = dict(ddim_sigmas=sigmas, ddim_alphas=alphas, ddim_alphas_prev=alphas_prev,
+                           ddim_sqrt_alphas=np.sqrt(alphas), ddim_sqrt_one_minus_alphas=np.sqrt(1.0 - alphas))
+
+    def _step_coefs(self):
+        tb = {k: torch.tensor(v, dtype=torch.float32) for k, v in self.tables.items()}
+        S = len(self.ddim_timesteps)
+        c = torch.zeros(S, 8, dtype=torch.float32)
+        c[:, 0] = tb["ddim_alphas"].sqrt()                                       # a_t.sqrt()
+        c[:, 1] = tb["ddim_sqrt_one_minus_alphas"]
+        c[:, 2] = tb["ddim_alphas_prev"].sqrt()
+        c[:, 3] = (1.0 - tb["ddim_alphas_prev"] - tb["ddim_sigmas"] ** 2).sqrt()
+        c[:, 4] = tb["ddim_sigmas"]
+        c[:, 5] = tb["ddim_sqrt_alphas"]
+        return self.ddim_timesteps, c, (2 if self.parameterization == "eps" else 3)

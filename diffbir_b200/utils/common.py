@@ -1,0 +1,70 @@
+"""Host-side helpers with the reference's names and semantics (diffbir/utils/common.py):
+sliding windows, Gaussian tile weights, wavelet colour fix, config instantiation."""
+from __future__ import annotations
+
+import importlib
+from typing import Any, List, Mapping, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def get_obj_from_str(string: str) -> Any:
+    module, cls = string.rsplit(".", 1)
+    if module == "diffbir.model" or module.startswith("diffbir.model."):
+        module = "diffbir_b200.model"          # reference YAML targets resolve to this package
+    return getattr(importlib.import_module(module), cls)
+
+
+def instantiate_from_config(config: Mapping[str, Any], **extra) -> Any:
+    """`target:` / `params:` reflection of utils/common.py:15-26 (same YAML files)."""
+    if "target" not in config:
+        raise KeyError("Expected key `target` to instantiate.")
+    return get_obj_from_str(config["target"])(**config.get("params", dict()), **extra)
+
+
+def sliding_windows(h: int, w: int, tile_size: int, tile_stride: int) -> List[Tuple[int, int, int, int]]:
+    """Row-major windows; the last one is snapped to the border (utils/common.py:123-138)."""
+    his = list(range(0, h - tile_size + 1, tile_stride))
+    if (h - tile_size) % tile_stride != 0:
+        his.append(h - tile_size)
+    wis = list(range(0, w - tile_size + 1, tile_stride))
+    if (w - tile_size) % tile_stride != 0:
+        wis.append(w - tile_size)
+    return [(hi, hi + tile_size, wi, wi + tile_size) for hi in his for wi in wis]
+
+
+def gaussian_weights(tile_width: int, tile_height: int) -> np.ndarray:
+    """Gaussian tile mask, var 0.01; x midpoint (W-1)/2, y midpoint H/2 — the asymmetry is the
+    reference's (utils/common.py:142-169) and is kept."""
+    var = 0.01
+    xs, ys = np.arange(tile_width), np.arange(tile_height)
+    xp = np.exp(-(xs - (tile_width - 1) / 2) ** 2 / (tile_width * tile_width) / (2 * var)) / np.sqrt(2 * np.pi * var)
+    yp = np.exp(-(ys - tile_height / 2) ** 2 / (tile_height * tile_height) / (2 * var)) / np.sqrt(2 * np.pi * var)
+    return np.outer(yp, xp)
+
+
+def wavelet_blur(image: torch.Tensor, radius: int) -> torch.Tensor:
+    k = torch.tensor([[0.0625, 0.125, 0.0625], [0.125, 0.25, 0.125], [0.0625, 0.125, 0.0625]],
+                     dtype=image.dtype, device=image.device)[None, None].repeat(3, 1, 1, 1)
+    image = F.pad(image, (radius, radius, radius, radius), mode="replicate")
+    return F.conv2d(image, k, groups=3, dilation=radius)
+
+
+def wavelet_decomposition(image: torch.Tensor, levels: int = 5):
+    high = torch.zeros_like(image)
+    low = image
+    for i in range(levels):
+        low = wavelet_blur(image, 2 ** i)
+        high = high + (image - low)
+        image = low
+    return high, low
+
+
+def wavelet_reconstruction(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
+    """High frequencies of the sample + low frequencies of the stage-1 image
+    (utils/common.py:66-77)."""
+    ch, _ = wavelet_decomposition(content_feat)
+    _, sl = wavelet_decomposition(style_feat)
+    return ch + sl

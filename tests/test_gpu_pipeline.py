@@ -1,0 +1,96 @@
+"""-m gpu: end-to-end parity of SwinIRPipeline.run (kernel engines, CUDA-graphed sampler) against
+the oracle's restatement of the reference pipeline run in fp32 (TF32 off) on the same device with
+the same seed (identical RNG consumption: x_T, then one randn_like per step).
+
+Bar (BASELINE.json north_star): PSNR >= 50 dB between the uint8 outputs of the full 50-step run.
+"""
+import numpy as np
+import pytest
+import torch
+
+from diffbir_b200 import arch
+from diffbir_b200.utils.synth import RUN_DEFAULTS, build_synthetic_pipeline, make_state_dict, synthetic_lq
+from tests.gpu_util import no_tf32, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_run(pipe, lq, small, seed=231, **kw):
+    """Oracle pipeline on the GPU in fp32 using the same state dicts the product loaded."""
+    from oracle import cldm as ocl
+    from oracle import sampling as osm
+    from oracle import swinir as osw
+    dev = "cuda"
+    cl = pipe.cldm
+    usd, csd, vsd = to_dev(cl._unet_sd), to_dev(cl._cn_sd), to_dev(cl._vae_sd)
+    clipsd = to_dev(cl._clip_sd)
+    ssd = to_dev({k: v for k, v in pipe.cleaner.engine_sd.items()})
+    heads = cl.clip_cfg["text_cfg"]["heads"]
+    scales = {"s": [1.0] * 13}
+
+    def model(x, t, cond):
+        return ocl.cldm_forward(usd, csd, x, t, cond["c_txt"], cond["c_img"], scales["s"])
+
+    torch.manual_seed(seed)
+    taps = {}
+    with torch.no_grad():
+        out = osm.swinir_pipeline_run(
+            lq, cleaner=lambda im: osw.swinir_forward(ssd, im),
+            encode_img=lambda im: ocl.vae_encode_mode(vsd, im, cl.scale_factor),
+            encode_txt=lambda txt: ocl.clip_text_encode(clipsd, cl.tokenize(txt).to(dev), heads=heads),
+            decode=lambda z: ocl.vae_decode(vsd, z / cl.scale_factor), model=model,
+            betas=pipe.diffusion.betas, parameterization=pipe.diffusion.parameterization,
+            steps=kw["steps"], strength=kw["strength"], pos_prompt=kw["pos_prompt"], neg_prompt=kw["neg_prompt"],
+            cfg_scale=kw["cfg_scale"], sampler=kw["sampler_type"], cldm_tiled=kw["cldm_tiled"],
+            cldm_tile_size=kw["cldm_tile_size"], cldm_tile_stride=kw["cldm_tile_stride"], device=dev,
+            set_strength=lambda s: scales.update(s=[s] * 13), taps=taps)
+    return out, taps
+
+
+def _psnr_u8(a, b):
+    mse = ((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean()
+    return float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def _pipe(small):
+    no_tf32()
+    pipe = build_synthetic_pipeline("cuda", seed=1234, small=small)
+    scfg = dict(arch.SWINIR_CFG, depths=(2, 2), num_heads=(6, 6)) if small else arch.SWINIR_CFG
+    pipe.cleaner.engine_sd = make_state_dict(arch.swinir_shapes(scfg), 1234 + 4)
+    pipe.taps = {}
+    return pipe
+
+
+@pytest.mark.parametrize("sampler,steps,tiled", [("spaced", 10, False), ("ddim", 10, False), ("spaced", 4, True)])
+def test_small_pipeline_matches_oracle(sampler, steps, tiled):
+    pipe = _pipe(True)
+    size = 640 if tiled else 512
+    lq = synthetic_lq(size, size, seed=1)
+    kw = dict(RUN_DEFAULTS, steps=steps, sampler_type=sampler, cldm_tiled=tiled)
+    torch.manual_seed(231)
+    out = pipe.run(lq, **kw)
+    ref, taps = _oracle_run(pipe, lq, True, **kw)
+    zp, zr = pipe.taps["z"], taps["z"]
+    e = ((zp - zr).pow(2).mean().sqrt() / zr.pow(2).mean().sqrt()).item()
+    p = _psnr_u8(out, ref)
+    print(f"small {sampler} x{steps} tiled={tiled}: latent rel-rms {e:.2e}, uint8 PSNR {p:.1f} dB, "
+          f"differing pixels {(out != ref).mean() * 100:.1f}%")
+    assert out.shape == ref.shape == lq.shape and out.dtype == np.uint8
+    assert e < 2e-2 and p > 45.0
+
+
+def test_full_config_50_step_psnr():
+    """BASELINE configs[1]: 512x512, 50-step spaced sampler, cfg 4.0, full SD-2.1 UNet + ControlNet."""
+    pipe = _pipe(False)
+    lq = synthetic_lq(512, 512, seed=0)
+    kw = dict(RUN_DEFAULTS)
+    torch.manual_seed(231)
+    out = pipe.run(lq, **kw)
+    ref, taps = _oracle_run(pipe, lq, False, **kw)
+    zp, zr = pipe.taps["z"], taps["z"]
+    e = ((zp - zr).pow(2).mean().sqrt() / zr.pow(2).mean().sqrt()).item()
+    p = _psnr_u8(out, ref)
+    print(f"FULL 512^2 50-step spaced: latent rel-rms {e:.2e}, uint8 PSNR {p:.2f} dB, differing pixels "
+          f"{(out != ref).mean() * 100:.1f}%, max |diff| {np.abs(out.astype(int) - ref.astype(int)).max()}, "
+          f"output mean {out.mean():.1f} std {out.std():.1f}")
+    assert p >= 50.0, f"PSNR {p:.2f} dB < 50 dB vs the fp32 reference path"
