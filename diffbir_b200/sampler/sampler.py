@@ -37,6 +37,25 @@ def space_timesteps(num_timesteps: int, steps: int) -> np.ndarray:
     return np.array(sorted(set(out)), dtype=np.int32)
 
 
+# ---- tile sharding (multi-GPU tiled sampling; host-side logic shared with the CPU/gloo test) ----
+def tiles_of_rank(num_tiles: int, rank: int, world: int) -> List[int]:
+    """Round-robin ownership: tile t belongs to rank t % world, local slot t // world."""
+    return list(range(rank, num_tiles, world))
+
+
+def tile_slots(num_tiles: int, world: int) -> int:
+    return (num_tiles + world - 1) // world
+
+
+def assemble_gathered(recv: torch.Tensor) -> torch.Tensor:
+    """all_gather output [world, nbr, slots, ...] -> [nbr, slots*world, ...] in global tile order
+    (tile t = slot*world + rank); entries >= num_tiles are padding."""
+    world, nbr, slots = recv.shape[:3]
+    rest = recv.shape[3:]
+    perm = (1, 2, 0) + tuple(range(3, recv.dim()))
+    return recv.permute(*perm).reshape(nbr, slots * world, *rest).contiguous()
+
+
 class Sampler:
     def __init__(self, betas: np.ndarray, parameterization: str, rescale_cfg: bool):
         self.num_timesteps = len(betas)
@@ -44,6 +63,7 @@ class Sampler:
         self.training_alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
         self.parameterization = parameterization
         self.rescale_cfg = rescale_cfg
+        self.shard_tiles = True     # tiled sampling: shard tiles over torch.distributed ranks
 
     def get_cfg_scale(self, default_cfg_scale: float, model_t: int) -> float:
         """Cosine CFG ramp — sampler/sampler.py:31-38."""
@@ -92,14 +112,15 @@ class Sampler:
         model_ts = [int(ts[i]) for i in order]
 
         import torch.distributed as dist
-        world, rank = (dist.get_world_size(), dist.get_rank()) if (tiled and dist.is_available() and dist.is_initialized()) else (1, 0)
+        world, rank = ((dist.get_world_size(), dist.get_rank())
+                       if (tiled and self.shard_tiles and dist.is_available() and dist.is_initialized()) else (1, 0))
 
         if tiled:
             wins = sliding_windows(H, W, tile_size, tile_stride)
             T = len(wins)
             all_coords = torch.tensor([[a, c] for a, _, c, _ in wins], dtype=torch.int32, device=dev)
-            mine = list(range(rank, T, world))                 # round-robin tile ownership
-            slots = (T + world - 1) // world
+            mine = tiles_of_rank(T, rank, world)               # round-robin tile ownership
+            slots = tile_slots(T, world)
             my_coords = all_coords[mine].contiguous()
             Tl, ts_ = len(mine), tile_size
             wts = torch.tensor(gaussian_weights(ts_, ts_), dtype=torch.float32, device=dev)
@@ -160,8 +181,7 @@ class Sampler:
                 if world > 1:
                     send[:, :Tl].copy_(ev)
                     dist.all_gather_into_tensor(recv, send)
-                    # [world, nbr, slots, ...] -> [nbr, slots, world, ...]: tile t = slot*world + rank
-                    tiles = recv.permute(1, 2, 0, 3, 4, 5, 6).reshape(nbr, slots * world, B, C, ts_, ts_).contiguous()
+                    tiles = assemble_gathered(recv)             # global tile order, padding at the end
                 else:
                     tiles = ev
                 for j in range(nbr):

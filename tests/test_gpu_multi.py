@@ -1,0 +1,23 @@
+"""-m gpu, >= 2 GPUs: tiled sampling sharded over NCCL ranks == single-rank tiled sampling,
+bit for bit (tools/run_tiled_multi.py under torchrun)."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_sharded_tiles_bit_identical():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(ROOT / "tools" / "run_tiled_multi.py")],
+                       capture_output=True, text=True, timeout=900)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0
