@@ -40,8 +40,9 @@ def _worker(rank, world, port, q):
     for s, t in enumerate(mine):
         a, b, c, d = wins[t]
         send[0, s] = _stub(x[..., a:b, c:d], 7, c_img[..., a:b, c:d])
-    recv = torch.empty(world, 1, slots, B, C, size, size)
-    dist.all_gather_into_tensor(recv, send)
+    parts = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(parts, send)                        # gloo: list form (NCCL path uses _into_tensor)
+    recv = torch.stack(parts, 0)
     tiles = assemble_gathered(recv)[0]                 # [slots*world, B, C, size, size]
     out, cnt = torch.zeros_like(x), torch.zeros_like(x)
     w = torch.tensor(gaussian_weights(size, size)[None, None], dtype=x.dtype)
