@@ -24,25 +24,30 @@ __device__ __forceinline__ const float* cat_ptr(const float* s1, const float* s2
   return c < c1 ? s1 + pix * c1 + c : s2 + pix * c2 + (c - c1);
 }
 
-// Stage 1: per-channel sum / sum of squares over a chunk of pixels.
-// grid = (chunks, N). partial layout: [N][chunks][C][2].
-// The last CTA of each image (atomic ticket) folds the partials into per-group mean / rstd.
+// Stage 1: per-group sum / sum of squares over a chunk of pixels.
+// grid = (chunks, N). A warp sweeps 128-channel slabs (one float4 per lane, coalesced) over the
+// chunk's pixels keeping per-lane register sums, folds them into 32 per-group shared-memory
+// accumulators, and the CTA writes 64 floats: partial[N][chunks][32][2].
+// The last CTA of each image (atomic ticket, self-resetting) combines the chunk partials in fp64
+// in a fixed order -> deterministic mean / rstd.
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int c1, int c2,
                 int hw, int pix_per_chunk, float* __restrict__ partial,
                 unsigned int* __restrict__ tickets, float* __restrict__ stats, float eps) {
   const int C = c1 + c2;
+  const int cpg = C / 32;
   const int n = blockIdx.y;
   const int chunk = blockIdx.x;
   const int chunks = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p_begin = chunk * pix_per_chunk;
   const int p_end = min(hw, p_begin + pix_per_chunk);
-  __shared__ float s_part[GN_WARPS][128][2];
+  __shared__ float s_grp[GN_WARPS][32][2];
+  __shared__ float s_ch[GN_WARPS][128][2];
   __shared__ bool s_last;
-  float* my_partial = partial + (static_cast<long long>(n) * chunks + chunk) * C * 2;
+  for (int i = threadIdx.x; i < GN_WARPS * 64; i += GN_THREADS) (&s_grp[0][0][0])[i] = 0.f;
+  __syncthreads();
 
-  // channel slabs of 128 (one float4 per lane)
   for (int cb = 0; cb < C; cb += 128) {
     const int c = cb + lane * 4;
     float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -55,24 +60,33 @@ gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
         sq[0] += v.x * v.x; sq[1] += v.y * v.y; sq[2] += v.z * v.z; sq[3] += v.w * v.w;
       }
     }
+    // fold the slab's channels into groups without atomics (fixed order => deterministic):
+    // lane l owns group (cb / cpg + l) for this slab
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      s_part[warp][lane * 4 + j][0] = sum[j];
-      s_part[warp][lane * 4 + j][1] = sq[j];
-    }
-    __syncthreads();
-    if (threadIdx.x < 128 && cb + threadIdx.x < C) {
+    for (int j = 0; j < 4; ++j) { s_ch[warp][lane * 4 + j][0] = sum[j]; s_ch[warp][lane * 4 + j][1] = sq[j]; }
+    __syncwarp();
+    const int g = cb / cpg + lane;
+    const int c_lo = max(g * cpg, cb), c_hi = min(min((g + 1) * cpg, cb + 128), C);
+    if (g < 32 && c_lo < c_hi) {
       float a = 0.f, b = 0.f;
-#pragma unroll
-      for (int w = 0; w < GN_WARPS; ++w) { a += s_part[w][threadIdx.x][0]; b += s_part[w][threadIdx.x][1]; }
-      my_partial[(cb + threadIdx.x) * 2 + 0] = a;
-      my_partial[(cb + threadIdx.x) * 2 + 1] = b;
+      for (int cc = c_lo; cc < c_hi; ++cc) { a += s_ch[warp][cc - cb][0]; b += s_ch[warp][cc - cb][1]; }
+      s_grp[warp][g][0] += a;
+      s_grp[warp][g][1] += b;
     }
-    __syncthreads();
+    __syncwarp();
+  }
+  __syncthreads();
+  float* my_partial = partial + (static_cast<long long>(n) * chunks + chunk) * 64;
+  if (threadIdx.x < 64) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < GN_WARPS; ++w) a += (&s_grp[w][0][0])[threadIdx.x];
+    my_partial[threadIdx.x] = a;
   }
 
-  // ---- last-CTA-of-the-image finalisation (deterministic: fixed summation order) ----
+  // ---- last-CTA-of-the-image finalisation (fixed summation order) ----
   __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(&tickets[n], 1u);
     s_last = (t == static_cast<unsigned int>(chunks) - 1);
@@ -81,16 +95,12 @@ gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int cpg = C / 32;
-  const float* img_partial = partial + static_cast<long long>(n) * chunks * C * 2;
+  const float* img_partial = partial + static_cast<long long>(n) * chunks * 64;
   for (int g = warp; g < 32; g += GN_WARPS) {
     double a = 0.0, b = 0.0;
-    const int total = chunks * cpg;
-    for (int i = lane; i < total; i += 32) {
-      const int ch = i / cpg, cc = g * cpg + i % cpg;
-      const float* q = img_partial + (static_cast<long long>(ch) * C + cc) * 2;
-      a += static_cast<double>(__ldcg(q));
-      b += static_cast<double>(__ldcg(q + 1));
+    for (int ch = lane; ch < chunks; ch += 32) {
+      a += static_cast<double>(__ldcg(img_partial + ch * 64 + g * 2));
+      b += static_cast<double>(__ldcg(img_partial + ch * 64 + g * 2 + 1));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -229,10 +239,9 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C,
 }  // namespace
 
 extern "C" int64_t dbir_gn_workspace_floats(int32_t n, int32_t hw, int32_t c) {
-  // partials [n][chunks][c][2] with chunks <= min(512, ceil(hw / 8)), plus tickets
-  int chunks = (hw + 7) / 8;
-  if (chunks > 512) chunks = 512;
-  return static_cast<int64_t>(n) * chunks * c * 2 + 64 + ((n + 3) / 4) * 4 + 64;
+  // tickets + partials [n][chunks <= 1024][32][2]
+  (void)hw; (void)c;
+  return 64 + ((static_cast<int64_t>(n) + 3) / 4) * 4 + static_cast<int64_t>(n) * 1024 * 64 + 64;
 }
 
 static int gn_chunks(int n, int hw, int* pix_per_chunk) {
@@ -242,7 +251,7 @@ static int gn_chunks(int n, int hw, int* pix_per_chunk) {
   int ppc = (hw + chunks - 1) / chunks;
   if (ppc < 8) ppc = 8;
   chunks = (hw + ppc - 1) / ppc;
-  if (chunks > 512) { chunks = 512; ppc = (hw + chunks - 1) / chunks; chunks = (hw + ppc - 1) / ppc; }
+  if (chunks > 1024) { chunks = 1024; ppc = (hw + chunks - 1) / chunks; chunks = (hw + ppc - 1) / ppc; }
   *pix_per_chunk = ppc;
   return chunks;
 }

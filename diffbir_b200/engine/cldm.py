@@ -141,6 +141,8 @@ class CldmEngine:
         self.emb_table: Optional[torch.Tensor] = None
         self.emb_offsets: Dict[str, int] = {}
         self._nb = 0
+        self.two_streams = True          # ControlNet || UNet encoder
+        self._side = None
 
     # ------------------------------------------------------------------ hoisted work
     def set_context(self, c_txt: torch.Tensor):
@@ -198,15 +200,20 @@ class CldmEngine:
         """Selects the time embedding of sampler step `step_idx` (one D2D copy, outside graphs)."""
         self.emb_cur.copy_(self.emb_table[step_idx])
 
+    def _gemm(self, tag: str, *args, **kw):
+        """dbir_gemm with this stream's split-K scratch (64 MiB, zero-initialised once)."""
+        ws = self.ws.get(tag + ":splitk", (16 * 1024 * 1024 + 16384,), torch.float32, zero=True)
+        lib.gemm(*args, splitk_ws=ws, **kw)
+
     def _emb(self, tag: str, l: arch.Layer, nb: int) -> torch.Tensor:
         o = self.emb_offsets[tag + l.prefix]
         return self.emb_cur[o:o + nb * l.cout]
 
     # ------------------------------------------------------------------ blocks
-    def _gn(self, src1, src2, c1, c2, nb, h, w, eps, gamma, beta, out16, silu, out_raw=None):
+    def _gn(self, tag, src1, src2, c1, c2, nb, h, w, eps, gamma, beta, out16, silu, out_raw=None):
         ws = self.ws
-        stats = ws.get("gn_stats", (nb * 64,), torch.float32)
-        wsp = ws.get("gn_ws", (lib.gn_workspace_floats(nb, h * w, c1 + c2),), torch.float32, zero=True)
+        stats = ws.get(tag + ":gn_stats", (nb * 64,), torch.float32)
+        wsp = ws.get(tag + ":gn_ws", (lib.gn_workspace_floats(nb, h * w, c1 + c2),), torch.float32, zero=True)
         lib.gn_stats(src1, src2, c1, c2, nb, h * w, eps, stats, wsp)
         lib.gn_apply(src1, src2, c1, c2, nb, h, w, stats, gamma, beta, out16, norm=True, silu=silu,
                      out_raw=out_raw)
@@ -215,23 +222,23 @@ class CldmEngine:
         """ResBlock._forward (unet.py:203-223): out may alias src1 when c2 == 0."""
         ws, W, p = self.ws, net.w, l.prefix
         cin, cout, M = c1 + c2, l.cout, nb * h * w
-        a16 = ws.get("res_a16", (M, cin), self.op_dtype)
-        raw16 = ws.get("res_raw16", (M, cin), self.op_dtype) if cin != cout else None
-        self._gn(src1, src2, c1, c2, nb, h, w, 1e-5, W[p + "in_layers.0.weight"],
+        a16 = ws.get(tag + ":res_a16", (M, cin), self.op_dtype)
+        raw16 = ws.get(tag + ":res_raw16", (M, cin), self.op_dtype) if cin != cout else None
+        self._gn(tag, src1, src2, c1, c2, nb, h, w, 1e-5, W[p + "in_layers.0.weight"],
                  W[p + "in_layers.0.bias"], a16, True, out_raw=raw16)
-        h1 = ws.get("res_h1", (M, cout), torch.float32)
-        lib.gemm(a16, W[p + "conv1.w"], h1, M=M, N=cout, K=9 * cin, bias=W[p + "conv1.b"],
+        h1 = ws.get(tag + ":res_h1", (M, cout), torch.float32)
+        self._gemm(tag, a16, W[p + "conv1.w"], h1, M=M, N=cout, K=9 * cin, bias=W[p + "conv1.b"],
                  rowvec=self._emb(tag, l, nb), conv=(nb, h, w, cin, 3))
-        b16 = ws.get("res_b16", (M, cout), self.op_dtype)
-        self._gn(h1, None, cout, 0, nb, h, w, 1e-5, W[p + "out_layers.0.weight"],
+        b16 = ws.get(tag + ":res_b16", (M, cout), self.op_dtype)
+        self._gn(tag, h1, None, cout, 0, nb, h, w, 1e-5, W[p + "out_layers.0.weight"],
                  W[p + "out_layers.0.bias"], b16, True)
         if cin != cout:
-            skip = ws.get("res_skip", (M, cout), torch.float32)
-            lib.gemm(raw16, W[p + "skip.w"], skip, M=M, N=cout, K=cin, bias=W[p + "skip.b"])
+            skip = ws.get(tag + ":res_skip", (M, cout), torch.float32)
+            self._gemm(tag, raw16, W[p + "skip.w"], skip, M=M, N=cout, K=cin, bias=W[p + "skip.b"])
             res = skip
         else:
             res = src1
-        lib.gemm(b16, W[p + "conv2.w"], out, M=M, N=cout, K=9 * cout, bias=W[p + "conv2.b"],
+        self._gemm(tag, b16, W[p + "conv2.w"], out, M=M, N=cout, K=9 * cout, bias=W[p + "conv2.b"],
                  residual=res, conv=(nb, h, w, cout, 3))
 
     def _attn(self, net: _Net, tag: str, l: arch.Layer, x, nb, h, w):
@@ -240,46 +247,46 @@ class CldmEngine:
         q = p + "transformer_blocks.0."
         c, M, hw = l.cin, nb * h * w, h * w
         heads = c // HEAD_DIM
-        a16 = ws.get("at_a16", (M, c), self.op_dtype)
-        self._gn(x, None, c, 0, nb, h, w, 1e-6, W[p + "norm.weight"], W[p + "norm.bias"], a16, False)
-        t = ws.get("at_t", (M, c), torch.float32)
-        lib.gemm(a16, W[p + "proj_in.w"], t, M=M, N=c, K=c, bias=W[p + "proj_in.b"])
+        a16 = ws.get(tag + ":at_a16", (M, c), self.op_dtype)
+        self._gn(tag, x, None, c, 0, nb, h, w, 1e-6, W[p + "norm.weight"], W[p + "norm.bias"], a16, False)
+        t = ws.get(tag + ":at_t", (M, c), torch.float32)
+        self._gemm(tag, a16, W[p + "proj_in.w"], t, M=M, N=c, K=c, bias=W[p + "proj_in.b"])
         # self-attention
         lib.layernorm(t, c, M, c, W[q + "norm1.weight"], W[q + "norm1.bias"], a16, c)
-        qkv = ws.get("at_qkv", (M, 3 * c), self.op_dtype)
-        lib.gemm(a16, W[q + "qkv.w"], qkv, M=M, N=3 * c, K=c)
-        att = ws.get("at_o16", (M, c), self.op_dtype)
+        qkv = ws.get(tag + ":at_qkv", (M, 3 * c), self.op_dtype)
+        self._gemm(tag, a16, W[q + "qkv.w"], qkv, M=M, N=3 * c, K=c)
+        att = ws.get(tag + ":at_o16", (M, c), self.op_dtype)
         lib.attention(qkv, qkv[:, c:], qkv[:, 2 * c:], att, batch=nb, heads=heads, sq=hw, skv=hw,
                       ldq=3 * c, ldk=3 * c, ldv=3 * c, ldo=c)
-        lib.gemm(att, W[q + "o1.w"], t, M=M, N=c, K=c, bias=W[q + "o1.b"], residual=t)
+        self._gemm(tag, att, W[q + "o1.w"], t, M=M, N=c, K=c, bias=W[q + "o1.b"], residual=t)
         # cross-attention on the (pre-projected) text context
         lib.layernorm(t, c, M, c, W[q + "norm2.weight"], W[q + "norm2.bias"], a16, c)
-        q16 = ws.get("at_q16", (M, c), self.op_dtype)
-        lib.gemm(a16, W[q + "q2.w"], q16, M=M, N=c, K=c)
+        q16 = ws.get(tag + ":at_q16", (M, c), self.op_dtype)
+        self._gemm(tag, a16, W[q + "q2.w"], q16, M=M, N=c, K=c)
         kv = self.kv[tag + l.prefix]
         lib.attention(q16, kv, kv[:, c:], att, batch=nb, heads=heads, sq=hw, skv=self.ctx_len,
                       ldq=c, ldk=2 * c, ldv=2 * c, ldo=c)
-        lib.gemm(att, W[q + "o2.w"], t, M=M, N=c, K=c, bias=W[q + "o2.b"], residual=t)
+        self._gemm(tag, att, W[q + "o2.w"], t, M=M, N=c, K=c, bias=W[q + "o2.b"], residual=t)
         # GEGLU feed-forward
         lib.layernorm(t, c, M, c, W[q + "norm3.weight"], W[q + "norm3.bias"], a16, c)
-        ffh = ws.get("at_ffh", (M, 4 * c), self.op_dtype)
-        lib.gemm(a16, W[q + "ff1.w"], ffh, M=M, N=8 * c, K=c, bias=W[q + "ff1.b"], geglu=True,
+        ffh = ws.get(tag + ":at_ffh", (M, 4 * c), self.op_dtype)
+        self._gemm(tag, a16, W[q + "ff1.w"], ffh, M=M, N=8 * c, K=c, bias=W[q + "ff1.b"], geglu=True,
                  force_bn=geglu_tile(c))
-        lib.gemm(ffh, W[q + "ff2.w"], a16, M=M, N=c, K=4 * c, bias=W[q + "ff2.b"], residual=t)
-        lib.gemm(a16, W[p + "proj_out.w"], x, M=M, N=c, K=c, bias=W[p + "proj_out.b"], residual=x)
+        self._gemm(tag, ffh, W[q + "ff2.w"], a16, M=M, N=c, K=4 * c, bias=W[q + "ff2.b"], residual=t)
+        self._gemm(tag, a16, W[p + "proj_out.w"], x, M=M, N=c, K=c, bias=W[p + "proj_out.b"], residual=x)
 
-    def _down(self, net: _Net, l: arch.Layer, x, nb, h, w, out):
+    def _down(self, net: _Net, tag: str, l: arch.Layer, x, nb, h, w, out):
         c, ho, wo = l.cin, h // 2, w // 2
-        col = self.ws.get("down_col", (nb * ho * wo, 9 * c), self.op_dtype)
+        col = self.ws.get(tag + ":down_col", (nb * ho * wo, 9 * c), self.op_dtype)
         lib.im2col_s2(x, nb, h, w, c, 1, col)
-        lib.gemm(col, net.w[l.prefix + "w"], out, M=nb * ho * wo, N=l.cout, K=9 * c,
+        self._gemm(tag, col, net.w[l.prefix + "w"], out, M=nb * ho * wo, N=l.cout, K=9 * c,
                  bias=net.w[l.prefix + "b"])
 
-    def _up(self, net: _Net, l: arch.Layer, x, nb, h, w, out):
+    def _up(self, net: _Net, tag: str, l: arch.Layer, x, nb, h, w, out):
         c = l.cin
         up16 = self.ws.get("up_a16", (nb * 4 * h * w, c), self.op_dtype)
         lib.gn_apply(x, None, c, 0, nb, h, w, None, None, None, up16, norm=False, silu=False, upsample=2)
-        lib.gemm(up16, net.w[l.prefix + "w"], out, M=nb * 4 * h * w, N=l.cout, K=9 * c,
+        self._gemm(tag, up16, net.w[l.prefix + "w"], out, M=nb * 4 * h * w, N=l.cout, K=9 * c,
                  bias=net.w[l.prefix + "b"], conv=(nb, 2 * h, 2 * w, c, 3))
 
     def _encoder(self, net: _Net, tag: str, x_in, hint, nb, h, w, keep: bool):
@@ -304,7 +311,7 @@ class CldmEngine:
                     self._attn(net, tag, l, cur, nb, ch, cw)
                 elif l.kind == "down":
                     o = ws.get(f"{tag}_hs{bi}", (nb * (ch // 2) * (cw // 2), l.cout), torch.float32)
-                    self._down(net, l, cur, nb, ch, cw, o)
+                    self._down(net, tag, l, cur, nb, ch, cw, o)
                     cur, cc, ch, cw = o, l.cout, ch // 2, cw // 2
             outs.append((cur, cc, ch, cw))
         mid = ws.get(f"{tag}_mid", (nb * ch * cw, cc), torch.float32)
@@ -325,21 +332,36 @@ class CldmEngine:
         nb, _, h, w = x.shape
         assert nb == self._nb == self.emb_nb, "set_context / set_timesteps batch mismatch"
         ws, U, Cn = self.ws, self.unet, self.cnet
-        # 1. UNet encoder + middle
-        hs, (mid, mc_, mh, mw) = self._encoder(U, "u", x, None, nb, h, w, True)
-        # 2. ControlNet; zero-convs accumulate into the UNet skips / middle in place
-        chs, (cmid, cmc, cmh, cmw) = self._encoder(Cn, "c", x, c_img, nb, h, w, False)
+        # 1+2. UNet encoder + middle on the current stream, ControlNet concurrently on a side
+        #      stream (their small 16x16 / 8x8 layers each fill only part of the 148 SMs);
+        #      fork/join with events so the pair is also captured as parallel graph branches.
+        main = torch.cuda.current_stream()
+        if self.two_streams:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side):
+                chs, (cmid, cmc, cmh, cmw) = self._encoder(Cn, "c", x, c_img, nb, h, w, False)
+                self._ev_join.record(self._side)
+            hs, (mid, mc_, mh, mw) = self._encoder(U, "u", x, None, nb, h, w, True)
+            main.wait_event(self._ev_join)
+        else:
+            hs, (mid, mc_, mh, mw) = self._encoder(U, "u", x, None, nb, h, w, True)
+            chs, (cmid, cmc, cmh, cmw) = self._encoder(Cn, "c", x, c_img, nb, h, w, False)
+        # zero-convs accumulate scale_i * (W h + b) into the UNet skips / middle in place
         for i, (t, c, th, tw) in enumerate(chs):
             M = nb * th * tw
             a16 = ws.get("zc_a16", (M, c), self.op_dtype)
             lib.gn_apply(t, None, c, 0, nb, th, tw, None, None, None, a16, norm=False, silu=False)
             tgt = hs[i][0]
-            lib.gemm(a16, Cn.w[f"zero_convs.{i}.w"], tgt, M=M, N=c, K=c, bias=Cn.w[f"zero_convs.{i}.b"],
+            self._gemm("u", a16, Cn.w[f"zero_convs.{i}.w"], tgt, M=M, N=c, K=c, bias=Cn.w[f"zero_convs.{i}.b"],
                      alpha=float(control_scales[i]), residual=tgt)
         M = nb * cmh * cmw
         a16 = ws.get("zc_a16", (M, cmc), self.op_dtype)
         lib.gn_apply(cmid, None, cmc, 0, nb, cmh, cmw, None, None, None, a16, norm=False, silu=False)
-        lib.gemm(a16, Cn.w["middle_block_out.w"], mid, M=M, N=cmc, K=cmc, bias=Cn.w["middle_block_out.b"],
+        self._gemm("u", a16, Cn.w["middle_block_out.w"], mid, M=M, N=cmc, K=cmc, bias=Cn.w["middle_block_out.b"],
                  alpha=float(control_scales[len(chs)]), residual=mid)
         # 3. UNet decoder over virtual concats
         cur, cc, ch, cw = mid, mc_, mh, mw
@@ -356,11 +378,11 @@ class CldmEngine:
                     self._attn(U, "u", l, cur, nb, ch, cw)
                 elif l.kind == "up":
                     o = ws.get(f"u_up{bi % 2}", (nb * 4 * ch * cw, l.cout), torch.float32)
-                    self._up(U, l, cur, nb, ch, cw, o)
+                    self._up(U, "u", l, cur, nb, ch, cw, o)
                     cur, cc, ch, cw = o, l.cout, ch * 2, cw * 2
         # 4. out = conv(silu(gn(h)))  (unet.py:675-679)
-        a16 = ws.get("res_a16", (nb * ch * cw, cc), self.op_dtype)
-        self._gn(cur, None, cc, 0, nb, ch, cw, 1e-5, U.w["out.0.weight"], U.w["out.0.bias"], a16, True)
+        a16 = ws.get("u:res_a16", (nb * ch * cw, cc), self.op_dtype)
+        self._gn("u", cur, None, cc, 0, nb, ch, cw, 1e-5, U.w["out.0.weight"], U.w["out.0.bias"], a16, True)
         oc = U.cfg["out_channels"]
         if out is None:
             out = torch.empty(nb, oc, ch, cw, dtype=torch.float32, device=self.dev)

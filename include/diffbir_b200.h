@@ -57,6 +57,11 @@ typedef struct dbir_gemm_args {
   int32_t reserved0;
   void* out2;           /* optional op16 copy of the result [rows, ldo2] (operand of the next op) */
   int64_t ldo2;
+  void* splitk_ws;      /* optional split-K scratch (zero-initialised once by the caller, >= 64 KiB +
+                           partial tiles); NULL disables split-K. Summation order is fixed. */
+  int64_t splitk_ws_bytes;
+  int32_t split_k;      /* 0 = auto, 1 = off, n > 1 = force n splits */
+  int32_t reserved1;
 } dbir_gemm_args;
 int dbir_gemm(const dbir_gemm_args* args, void* stream);
 

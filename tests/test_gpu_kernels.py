@@ -250,3 +250,27 @@ def test_sampler_step_and_tiles_bit_exact(L, golden_dir):
         acc[..., a:b_, c:d] += tiles[i] * wts
         cnt[..., a:b_, c:d] += wts
     assert torch.equal(blended, acc / cnt)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,split", [(2, 8, 8, 1280, 1280, 0), (2, 8, 8, 1280, 1280, 7),
+                                                   (2, 16, 16, 1280, 1280, 3), (1, 8, 8, 2560, 1280, 0)])
+def test_gemm_split_k_deterministic(L, n, h, w, cin, cout, split):
+    """Split-K (small-M, long-K layers): same result as the fp32 reference, bit-identical across
+    runs (fixed summation order), workspace tickets self-reset."""
+    dt = L.operand_dtype()
+    x = rnd(n, h, w, cin, seed=1).to(dt)
+    wt = rnd(cout, cin, 3, 3, seed=2, scale=(cin * 9) ** -0.5).to(dt)
+    bias, res = rnd(cout, seed=3), rnd(n * h * w, cout, seed=5)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    ws = torch.zeros(16 * 1024 * 1024 + 16384, device="cuda")
+    outs = []
+    for _ in range(3):
+        out = torch.empty(n * h * w, cout, device="cuda")
+        L.gemm(x, wp, out, M=n * h * w, N=cout, K=9 * cin, bias=bias, residual=res, conv=(n, h, w, cin, 3),
+               splitk_ws=ws, split_k=split)
+        outs.append(out)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(n * h * w, cout) + res
+    assert rel_err(outs[0], ref) < 3e-5
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert (ws[:16384] == 0).all()
