@@ -74,7 +74,7 @@ void dbir_set_error(const char* fmt, ...);
 
 // Encodes a tiled TMA descriptor (driver entry point fetched at run time, so the
 // library does not link libcuda). rank <= 5; dims/box innermost first; strides in
-// bytes for dims 1..rank-1. 16-bit elements, 128B swizzle unless swizzle==0.
+// bytes for dims 1..rank-1. swizzle: 0 none, 1 128B, 2 64B, 3 32B.
 int dbir_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes,
                    int swizzle128);

@@ -9,18 +9,25 @@
 // swinir.py:472,797-811). B is the packed weight [N, K] (K = taps*C, tap-major).
 //
 // One CTA computes a 128 x BN tile: warp 0 = TMA producer, warp 1 = MMA issuer,
-// warp 2 = TMEM allocator + epilogue, warps 3..5 = epilogue (thread == accumulator
-// row). Fused epilogue: bias, per-image row vector (time embedding), GELU /
-// LeakyReLU, GEGLU gating, alpha scaling and fp32 residual add
-// (out = res + alpha * f(acc + bias + rowvec)), fp32 or 16-bit output.
+// warp 2 = TMEM allocator + epilogue, warps 3..5 = epilogue (thread == accumulator row).
+//
+// Epilogue (per warp, 32 rows x 32 columns at a time): tcgen05.ld -> bias / per-image row
+// vector (time embedding) / GELU / LeakyReLU / SiLU / GEGLU gating / alpha -> + fp32 residual
+// tile (TMA-loaded, double buffered) -> swizzled shared-memory tile -> TMA bulk store
+// (double buffered). Threads never touch global memory for the output: with one epilogue warp
+// per scheduler every extra instruction is exposed latency, and the TMA unit also clips
+// overhanging rows / columns (M, N tails, conv tiles that overhang the image).
+//   out = residual + alpha * act(acc + bias + rowvec),  fp32 or 16-bit, any row stride.
 #include "common.cuh"
 #include "../../include/diffbir_b200.h"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 x 16-bit = 128 B = one swizzle atom row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int EPI_TILE_BYTES = 32 * 32 * 4;   // one warp's 32x32 fp32 staging tile
 
 struct GemmParams {
   int M, N, num_kb;
@@ -31,61 +38,138 @@ struct GemmParams {
   int tiles_x, tiles_y;    // tiles per image row / column
   int cblocks;             // C / 64
   int kw, pad;             // filter width (taps = kw*kw), padding
+  int wbw, wbh;            // per-warp sub-box (32 rows) extents in w / h
   // epilogue
-  void* out;
-  long long ldo;
   int out_kind;            // 0 fp32, 1 16-bit operand
   const float* bias;
   const float* rowvec;     // [NI or M/rows_per_vec, N]
   int rows_per_vec;
-  const float* residual;
-  long long ldr;
+  int has_residual;
   float alpha;
   int act;                 // 0 none, 1 gelu(erf), 2 leaky relu (slope in act_param), 3 silu
   float act_param;
   int geglu;               // 1: tile holds [BN/2 values | BN/2 gates]; output width N/2
   int bias_per_row;        // bias indexed by output row instead of column
-  void* out2;              // optional second copy of the result as op16 [rows, ldo2]
-  long long ldo2;
   // split-K: grid.z CTAs share one output tile; partial tiles go through `ws`, the last CTA to
   // arrive (ticket) sums them in fixed order (deterministic) and runs the epilogue.
   int splits, kb_per_split;
   float* ws;
   unsigned int* tickets;
+  long long* dbg;          // optional per-CTA clock64 stamps [ctas][4]: start, setup done, acc ready, end
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float prm) {
   if (act == 1) return gelu_erf_f(v);
   if (act == 2) return v > 0.f ? v : v * prm;
-  if (act == 3) return silu_f(v);
-  return v;
+  return silu_f(v);
 }
 
-// Epilogue for 32 consecutive accumulator columns x the warp's 32 rows.
-// Math (bias / time-embedding row vector / activation / alpha) runs in the accumulator layout
-// (thread == row). The chunk is then transposed through a padded per-warp shared-memory tile so
-// that the residual read and every store touch whole contiguous row segments (one 128-byte
-// line per warp instruction for fp32, 64 bytes x 2 rows for 16-bit) instead of 32 scattered rows.
-__device__ __forceinline__ void store_chunk(const GemmParams& p, float* v, float* T, int lane,
-                                            long long out_row, int gc0, int ncols);
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 
-__device__ __forceinline__ void finish_chunk(const GemmParams& p, float* v, float* T, int lane,
-                                             long long out_row, int vec_idx, int gc0, int ncols) {
-  if (out_row >= 0) {
+// Per-warp epilogue state: which 32 rows of the tile, their sub-box origin, staging buffers.
+struct EpiCtx {
+  const CUtensorMap* tm_out;
+  const CUtensorMap* tm_res;
+  uint32_t epi_base;       // shared address of this warp's 4 staging tiles: out[0], out[1], res[0], res[1]
+  uint32_t res_bar;        // shared address of this warp's two residual-load mbarriers
+  int row0;                // plain mode: first global row of this warp
+  int x, y, n;             // conv mode: origin of this warp's sub-box
+  __device__ __forceinline__ uint32_t out_buf(int b) const { return epi_base + b * EPI_TILE_BYTES; }
+  __device__ __forceinline__ uint32_t res_buf(int b) const { return epi_base + (2 + b) * EPI_TILE_BYTES; }
+  __device__ __forceinline__ uint32_t bar(int b) const { return res_bar + b * 8; }
+};
+
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 4000000000LL) { printf("dbir: residual mbarrier timeout\n"); __trap(); }
+  }
+}
+
+__device__ __forceinline__ void epi_issue_residual(const GemmParams& p, EpiCtx& e, int lane, int chunk_idx,
+                                                   int gc0) {
+  // lane 0 only
+  if (lane == 0) {
+    const int b = chunk_idx & 1;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(e.bar(b)), "r"(EPI_TILE_BYTES) : "memory");
+    if (p.mode == 0) {
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+              "r"(e.res_buf(b)), "l"(reinterpret_cast<uint64_t>(e.tm_res)), "r"(e.bar(b)), "r"(gc0), "r"(e.row0)
+          : "memory");
+    } else {
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+              "r"(e.res_buf(b)), "l"(reinterpret_cast<uint64_t>(e.tm_res)), "r"(e.bar(b)), "r"(gc0), "r"(e.x),
+          "r"(e.y), "r"(e.n)
+          : "memory");
+    }
+  }
+}
+
+// Finishes one 32-column chunk held as fp32 in v[] (thread == row): epilogue math, residual,
+// staging, TMA store. `chunk_idx` counts chunks processed by this warp (buffer parity),
+// `gc0` is the first *output* column, `next_gc0` (< 0: none) the column of the chunk after next
+// whose residual tile can start loading into the buffer this chunk frees.
+__device__ __forceinline__ void finish_chunk(const GemmParams& p, EpiCtx& e, float* v, int lane, int chunk_idx,
+                                             int gc0, int ncols, int next_gc0, long long out_row, int vec_idx,
+                                             bool raw_math) {
+  const int b = chunk_idx & 1;
+  if (raw_math) {
     if (p.bias) {
       if (p.bias_per_row) {
-        const float bv = __ldg(p.bias + out_row);
+        const float bv = out_row >= 0 ? __ldg(p.bias + out_row) : 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += bv;
+      } else if (ncols == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + gc0 + j));
+          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gc0 + j);
       }
     }
-    if (p.rowvec) {
+    if (p.rowvec && out_row >= 0) {
       const float* rv = p.rowvec + static_cast<long long>(vec_idx) * p.N + gc0;
+      if (ncols == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(rv + j);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(rv + j));
+          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(rv + j);
+      }
     }
     if (p.act) {
 #pragma unroll
@@ -96,60 +180,53 @@ __device__ __forceinline__ void finish_chunk(const GemmParams& p, float* v, floa
       for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
     }
   }
-  store_chunk(p, v, T, lane, out_row, gc0, ncols);
-}
-
-__device__ __forceinline__ void store_chunk(const GemmParams& p, float* v, float* T, int lane,
-                                            long long out_row, int gc0, int ncols) {
+  const int sw = lane & 7;
+  if (p.has_residual) {
+    mbar_wait_s(e.bar(b), (chunk_idx >> 1) & 1);
+    const uint32_t rrow = e.res_buf(b) + lane * 128;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) T[lane * 33 + j] = v[j];
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = lds_v4(rrow + ((j ^ sw) << 4));
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+    fence_proxy_async_smem();                       // generic reads before the async overwrite
+    __syncwarp();                                   // every lane has read the residual tile
+    if (next_gc0 >= 0) epi_issue_residual(p, e, lane, chunk_idx + 2, next_gc0);
+  }
+  // the store that used this staging buffer two chunks ago must have finished reading it
+  if (lane == 0 && chunk_idx >= 2) bulk_wait_read<1>();
   __syncwarp();
   if (p.out_kind == 0) {
-    float* out = reinterpret_cast<float*>(p.out);
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-      const long long orow = __shfl_sync(0xffffffffu, out_row, i);
-      if (orow >= 0 && lane < ncols) {
-        float val = T[i * 33 + lane];
-        if (p.residual) val += p.residual[orow * p.ldr + gc0 + lane];
-        out[orow * p.ldo + gc0 + lane] = val;
-        if (p.out2) reinterpret_cast<op_t*>(p.out2)[orow * p.ldo2 + gc0 + lane] = f2op(val);
-      }
-    }
+    const uint32_t orow = e.out_buf(b) + lane * 128;          // 128-byte rows, SWIZZLE_128B
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_v4(orow + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+             __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
   } else {
-    op_t* out = reinterpret_cast<op_t*>(p.out);
-    const int sub = lane >> 4, col = (lane & 15) * 2;
-#pragma unroll 4
-    for (int i = 0; i < 32; i += 2) {
-      const long long orow = __shfl_sync(0xffffffffu, out_row, i + sub);
-      if (orow >= 0 && col < ncols) {
-        float a = T[(i + sub) * 33 + col], b = T[(i + sub) * 33 + col + 1];
-        const bool two = col + 1 < ncols;
-        if (p.residual) {
-          const float* rs = p.residual + orow * p.ldr + gc0 + col;
-          a += rs[0];
-          if (two) b += rs[1];
-        }
-        op_t* o = out + orow * p.ldo + gc0 + col;
-        if (two) *reinterpret_cast<uint32_t*>(o) = pack2(a, b);
-        else *o = f2op(a);
-        if (p.out2) {
-          op_t* o2 = reinterpret_cast<op_t*>(p.out2) + orow * p.ldo2 + gc0 + col;
-          if (two) *reinterpret_cast<uint32_t*>(o2) = pack2(a, b);
-          else *o2 = f2op(a);
-        }
-      }
-    }
+    const uint32_t orow = e.out_buf(b) + lane * 64;           // 64-byte rows, SWIZZLE_64B
+    const int sw2 = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts_v4(orow + ((j ^ sw2) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+             pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
   }
+  fence_proxy_async_smem();
   __syncwarp();
+  if (lane == 0) {
+    if (p.mode == 0) tma_store_2d(e.tm_out, e.out_buf(b), gc0, e.row0);
+    else tma_store_4d(e.tm_out, e.out_buf(b), gc0, e.x, e.y, e.n);
+    bulk_commit();
+  }
 }
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
                const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static_assert(STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) >= 16 * EPI_TILE_BYTES, "epilogue staging must fit in the pipeline stages");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -158,7 +235,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* res_bars = tmem_full + 1;                 // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + 8);
   uint32_t* split_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
@@ -168,6 +246,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+  long long t_start = 0, t_setup = 0, t_acc = 0;
+  if (p.dbg) t_start = clock64();
 
   // tile origin
   int n0 = 0, y0 = 0, x0 = 0;
@@ -181,10 +261,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_out);
+    if (p.has_residual) tma_prefetch_desc(&tma_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&res_bars[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -192,6 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.dbg) t_setup = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -235,8 +319,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 -------------
     const int q = warp & 3;
     const int r = q * 32 + lane;            // accumulator row within the tile
-    long long out_row = -1;                 // global output row, -1 = masked
+    long long out_row = -1;                 // global output row (bias_per_row / rowvec index), -1 = masked
     int vec_idx = 0;
+    EpiCtx e;
+    e.tm_out = &tma_out; e.tm_res = &tma_res;
+    e.res_bar = smem_u32(res_bars + q * 2);
+    e.row0 = m_tile * BM + q * 32;
+    e.x = e.y = e.n = 0;
     if (p.mode == 0) {
       const long long gr = static_cast<long long>(m_tile) * BM + r;
       if (gr < p.M) { out_row = gr; vec_idx = static_cast<int>(gr / p.rows_per_vec); }
@@ -249,21 +338,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         out_row = (static_cast<long long>(n) * p.H + y) * p.W + x;
         vec_idx = n;
       }
+      const int r0 = q * 32;                // this warp's sub-box origin
+      e.x = x0 + r0 % p.bw;
+      e.y = y0 + (r0 / p.bw) % p.bh;
+      e.n = n0 + r0 / (p.bw * p.bh);
     }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (p.dbg) t_acc = clock64();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    // all MMAs have retired -> the pipeline stages are free: per-warp 32x33 fp32 transpose tiles
-    float* T = reinterpret_cast<float*>(sA) + (warp - 2) * (32 * 33 + 31);
+    // all MMAs have retired -> the pipeline stages are free: 4 staging tiles (4 KB) per warp
+    e.epi_base = smem_u32(sA) + q * (4 * EPI_TILE_BYTES);
 
+    constexpr int OUT_COLS = BN;            // accumulator columns that produce output (GEGLU: BN/2)
+    const bool finalize = p.splits == 1;
     if (!p.geglu) {
+      const int col_base = n_tile * BN;
+      // prefetch the first two residual tiles
+      if (finalize && p.has_residual) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          if (c * 32 < OUT_COLS && col_base + c * 32 < p.N) epi_issue_residual(p, e, lane, c, col_base + c * 32);
+      }
+      int ci = 0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t acc[32];
         __syncwarp();
         tmem_ld32(taddr + c0, acc);
         tmem_ld_wait();
-        const int gc0 = n_tile * BN + c0;
+        const int gc0 = col_base + c0;
         if (p.splits > 1) {
           // raw partial -> workspace [tile][split][col][row]: coalesced across the warp's rows
           float* wcol = p.ws + ((static_cast<long long>(tile_lin) * p.splits + blockIdx.z) * BN + c0) * BM + r;
@@ -273,10 +377,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (gc0 >= p.N) continue;
         const int ncols = min(32, p.N - gc0);
+        const int ngc = gc0 + 64;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-        finish_chunk(p, v, T, lane, out_row, vec_idx, gc0, ncols);
+        finish_chunk(p, e, v, lane, ci, gc0, ncols, (c0 + 64 < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true);
+        ++ci;
       }
       if (p.splits > 1) {
         __threadfence();
@@ -290,11 +396,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (*split_flag) {
           __threadfence();
+          if (p.has_residual) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              if (c * 32 < BN && col_base + c * 32 < p.N) epi_issue_residual(p, e, lane, c, col_base + c * 32);
+          }
+          int cj = 0;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 32) {
-            const int gc0 = n_tile * BN + c0;
+            const int gc0 = col_base + c0;
             if (gc0 >= p.N) continue;
             const int ncols = min(32, p.N - gc0);
+            const int ngc = gc0 + 64;
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -303,7 +416,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += __ldcg(wcol + j * BM);
             }
-            finish_chunk(p, v, T, lane, out_row, vec_idx, gc0, ncols);
+            finish_chunk(p, e, v, lane, cj, gc0, ncols, (c0 + 64 < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true);
+            ++cj;
           }
         }
       }
@@ -313,6 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr int HB = BN / 2;
       const int n_half = p.N / 2;
       if constexpr (HB % 32 == 0) {
+        int ci = 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < HB; c0 += 32) {
           uint32_t av[32], ag[32];
@@ -334,11 +449,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             v[j] = a * gelu_erf_f(g);
           }
-          store_chunk(p, v, T, lane, out_row, gc0, ncols);
+          finish_chunk(p, e, v, lane, ci, gc0, ncols, -1, out_row, vec_idx, false);
+          ++ci;
         }
       }
     }
+    if (lane == 0) bulk_wait_read<0>();     // staging tiles must outlive the bulk stores' reads
+    __syncwarp();
     tc_fence_before();
+    if (p.dbg && threadIdx.x == 64) {
+      long long* d = p.dbg + 8LL * ((static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+      d[0] = t_start; d[1] = t_setup; d[2] = t_acc; d[3] = clock64();
+    }
   }
   __syncthreads();
   if (warp == 2) {
@@ -348,8 +470,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 template <int BN, int STAGES>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
-           cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+           const GemmParams& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
@@ -357,7 +479,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, di
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  gemm_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ta, tb, p);
+  gemm_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ta, tb, to, tr, p);
   DBIR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -409,23 +531,28 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
                a->N, a->K);
   DBIR_REQUIRE(a->a && a->b && a->out, "dbir_gemm: null pointer");
   DBIR_REQUIRE(a->K % 8 == 0, "dbir_gemm: K=%d must be a multiple of 8 (16-byte rows)", a->K);
-  DBIR_REQUIRE(a->out_kind == 0 || (a->ldo % 2 == 0), "dbir_gemm: 16-bit output needs an even ldo");
-  DBIR_REQUIRE(!a->out2 || (a->ldo2 % 2 == 0), "dbir_gemm: out2 needs an even ldo2");
+  DBIR_REQUIRE(!a->out2, "dbir_gemm: out2 is not supported by the TMA-store epilogue");
+  const int eb = a->out_kind == 0 ? 4 : 2;
+  DBIR_REQUIRE((a->ldo * eb) % 16 == 0, "dbir_gemm: output row stride must be a multiple of 16 bytes (ldo=%lld)",
+               (long long)a->ldo);
+  DBIR_REQUIRE(!a->residual || a->ldr % 4 == 0, "dbir_gemm: residual row stride must be a multiple of 4");
 
   GemmParams p{};
   p.M = a->M; p.N = a->N;
   p.mode = a->a_mode;
-  p.out = a->out; p.ldo = a->ldo; p.out_kind = a->out_kind;
+  p.out_kind = a->out_kind;
   p.bias = a->bias; p.rowvec = a->rowvec;
   p.rows_per_vec = a->rows_per_vec > 0 ? a->rows_per_vec : a->M;
-  p.residual = a->residual; p.ldr = a->ldr;
+  p.has_residual = a->residual != nullptr;
   p.alpha = a->alpha; p.act = a->act; p.act_param = a->act_param; p.geglu = a->geglu;
-  p.bias_per_row = a->bias_per_row; p.out2 = a->out2; p.ldo2 = a->ldo2;
+  p.bias_per_row = a->bias_per_row;
+  p.dbg = reinterpret_cast<long long*>(a->debug_stamps);
   if (a->geglu)
-    DBIR_REQUIRE(a->force_bn >= 64 && a->force_bn != 160 && a->N % a->force_bn == 0,
+    DBIR_REQUIRE(a->force_bn >= 64 && a->force_bn != 160 && a->N % a->force_bn == 0 && !a->residual,
                  "dbir_gemm: GEGLU needs force_bn in {64,128,256} dividing N (weights are packed per tile)");
+  const int n_out = a->geglu ? a->N / 2 : a->N;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to, tr;
   int m_tiles;
   if (a->a_mode == 0) {
     const long long lda = a->lda > 0 ? a->lda : a->K;
@@ -436,6 +563,16 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
     if (dbir_make_tmap(&ta, a->a, 2, dims, strides, box, 2, 1)) return -3;
     p.num_kb = (a->K + BK - 1) / BK;
     m_tiles = (a->M + BM - 1) / BM;
+    // output / residual: 32 x 32 element boxes per epilogue warp
+    uint64_t odims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(a->M)};
+    uint64_t ostr[1] = {static_cast<uint64_t>(a->ldo) * eb};
+    uint32_t obox[2] = {32, 32};
+    if (dbir_make_tmap(&to, a->out, 2, odims, ostr, obox, eb, eb == 4 ? 1 : 2)) return -3;
+    tr = to;
+    if (a->residual) {
+      uint64_t rstr[1] = {static_cast<uint64_t>(a->ldr) * 4};
+      if (dbir_make_tmap(&tr, a->residual, 2, odims, rstr, obox, 4, 1)) return -3;
+    }
   } else {
     const int C = a->img_c, H = a->img_h, W = a->img_w, NI = a->img_n;
     const int taps = a->ksize * a->ksize;
@@ -463,6 +600,23 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
     if (dbir_make_tmap(&ta, a->a, 4, dims, strides, box, 2, 1)) return -3;
     p.num_kb = taps * p.cblocks;
     m_tiles = p.tiles_x * p.tiles_y * ((NI + bni - 1) / bni);
+    // per-warp sub-box of 32 pixels: (wbw x wbh x wbn)
+    const int wbw = bw < 32 ? bw : 32;
+    const int wbh = bh < 32 / wbw ? bh : 32 / wbw;
+    const int wbn = 32 / (wbw * wbh);
+    p.wbw = wbw; p.wbh = wbh;
+    uint64_t odims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                         static_cast<uint64_t>(NI)};
+    uint64_t ostr[3] = {static_cast<uint64_t>(a->ldo) * eb, static_cast<uint64_t>(W) * a->ldo * eb,
+                        static_cast<uint64_t>(H) * W * a->ldo * eb};
+    uint32_t obox[4] = {32, static_cast<uint32_t>(wbw), static_cast<uint32_t>(wbh), static_cast<uint32_t>(wbn)};
+    if (dbir_make_tmap(&to, a->out, 4, odims, ostr, obox, eb, eb == 4 ? 1 : 2)) return -3;
+    tr = to;
+    if (a->residual) {
+      uint64_t rstr[3] = {static_cast<uint64_t>(a->ldr) * 4, static_cast<uint64_t>(W) * a->ldr * 4,
+                          static_cast<uint64_t>(H) * W * a->ldr * 4};
+      if (dbir_make_tmap(&tr, a->residual, 4, odims, rstr, obox, 4, 1)) return -3;
+    }
   }
 
   constexpr long long TICKET_FLOATS = 16384;
@@ -483,15 +637,12 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
     if (dbir_make_tmap(&tb, a->b, 2, dims, strides, box, 2, 1)) return -3;
   }
   dim3 grid(m_tiles, (a->N + bn - 1) / bn, plan.splits);
-  // <= one CTA per SM anyway: use the whole 227 KB for a deep TMA pipeline (the mainloop is
-  // latency/feed bound); otherwise 3-5 stages so two CTAs share an SM (epilogue overlap).
-  const bool deep = static_cast<long long>(grid.x) * grid.y * grid.z <= dbir_sm_count();
   switch (bn) {
-    case 32:  return deep ? launch<32, 11>(ta, tb, p, grid, st) : launch<32, 5>(ta, tb, p, grid, st);
-    case 64:  return deep ? launch<64, 9>(ta, tb, p, grid, st) : launch<64, 4>(ta, tb, p, grid, st);
-    case 128: return deep ? launch<128, 7>(ta, tb, p, grid, st) : launch<128, 3>(ta, tb, p, grid, st);
-    case 160: return deep ? launch<160, 6>(ta, tb, p, grid, st) : launch<160, 3>(ta, tb, p, grid, st);
-    case 256: return launch<256, 4>(ta, tb, p, grid, st);
+    case 32:  return launch<32, 5>(ta, tb, to, tr, p, grid, st);
+    case 64:  return launch<64, 4>(ta, tb, to, tr, p, grid, st);
+    case 128: return launch<128, 3>(ta, tb, to, tr, p, grid, st);
+    case 160: return launch<160, 3>(ta, tb, to, tr, p, grid, st);
+    case 256: return launch<256, 4>(ta, tb, to, tr, p, grid, st);
     default:
       dbir_set_error("dbir_gemm: unsupported tile width %d", bn);
       return -2;

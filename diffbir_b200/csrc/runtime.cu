@@ -83,7 +83,9 @@ int dbir_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t*
                                            : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUresult r = enc(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr,
                    bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                   : swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                   : swizzle128 == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     dbir_set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu/%llu, box %u/%u)",

@@ -143,6 +143,10 @@ class CldmEngine:
         self._nb = 0
         self.two_streams = True          # ControlNet || UNet encoder
         self._side = None
+        self._ts_key = None
+        self.emb_cur = None
+        self._graphs = {}                # (shape, scales) -> (CUDAGraph, x_in, c_img, eps, launches)
+        self.ws.on_grow = self._graphs.clear
 
     # ------------------------------------------------------------------ hoisted work
     def set_context(self, c_txt: torch.Tensor):
@@ -159,12 +163,16 @@ class CldmEngine:
                 if buf is None or buf.shape[0] != nb * L:
                     buf = torch.empty(nb * L, 2 * l.cin, dtype=self.op_dtype, device=self.dev)
                     self.kv[key] = buf
+                    self._graphs.clear()
                 lib.gemm(ctx16, net.w[q + "kv2.w"], buf, M=nb * L, N=2 * l.cin, K=d)
 
     def set_timesteps(self, timesteps: Sequence[int], nb: int):
         """Time-embedding MLP + emb_layers of every ResBlock for every sampler step.
         Table layout: [steps][ per ResBlock r: nb x Cout_r ] fp32 (rows replicated over the
-        batch so each step needs a single device-to-device copy)."""
+        batch so each step needs a single device-to-device copy). Cached per (schedule, batch)."""
+        key = (tuple(int(t) for t in timesteps), nb)
+        if key == self._ts_key:
+            return
         S = len(timesteps)
         t = torch.tensor([float(x) for x in timesteps], dtype=torch.float32, device=self.dev)
         offs, total = {}, 0
@@ -180,21 +188,25 @@ class CldmEngine:
             h1 = torch.empty(S, emb_dim, dtype=torch.float32, device=self.dev)
             lib.linear_f32(te, self.mc, S, self.mc, net.w["time_embed.0.weight"],
                            net.w["time_embed.0.bias"], emb_dim, h1, emb_dim, silu_out=True)
-            emb = torch.empty(S, emb_dim, dtype=torch.float32, device=self.dev)
+            # every consumer is emb_layers = SiLU -> Linear (unet.py:166-172): apply the SiLU once
+            emb_act = torch.empty(S, emb_dim, dtype=torch.float32, device=self.dev)
             lib.linear_f32(h1, emb_dim, S, emb_dim, net.w["time_embed.2.weight"],
-                           net.w["time_embed.2.bias"], emb_dim, emb, emb_dim)
+                           net.w["time_embed.2.bias"], emb_dim, emb_act, emb_dim, silu_out=True)
             tmp = torch.empty(S, max(l.cout for l in net.res_layers), dtype=torch.float32, device=self.dev)
             for l in net.res_layers:
                 o = offs[tag + l.prefix]
                 y = tmp[:, : l.cout]
-                lib.linear_f32(emb, emb_dim, S, emb_dim, net.w[l.prefix + "emb.w"],
-                               net.w[l.prefix + "emb.b"], l.cout, y, tmp.shape[1], silu_in=True)
+                lib.linear_f32(emb_act, emb_dim, S, emb_dim, net.w[l.prefix + "emb.w"],
+                               net.w[l.prefix + "emb.b"], l.cout, y, tmp.shape[1])
                 table[:, o:o + nb * l.cout] = y.repeat(1, nb)
         self.emb_table = table
         self.emb_offsets = offs
         self.emb_nb = nb
-        self.emb_cur = torch.empty(total, dtype=torch.float32, device=self.dev)
+        if self.emb_cur is None or self.emb_cur.numel() != total:
+            self.emb_cur = torch.empty(total, dtype=torch.float32, device=self.dev)
+            self._graphs.clear()            # graphs hold the old buffer's address
         self.timesteps = list(timesteps)
+        self._ts_key = key
 
     def load_step(self, step_idx: int):
         """Selects the time embedding of sampler step `step_idx` (one D2D copy, outside graphs)."""
@@ -320,6 +332,29 @@ class CldmEngine:
         self._attn(net, tag, m[1], mid, nb, ch, cw)
         self._res(net, tag, m[2], mid, None, cc, 0, nb, ch, cw, mid)
         return outs, (mid, cc, ch, cw)
+
+    # ------------------------------------------------------------------ CUDA graph of one forward
+    def graphed_forward(self, nb: int, c: int, h: int, w: int, control_scales: Sequence[float]):
+        """Returns (graph, x_in, c_img, eps, kernels_per_replay): static input/output buffers and
+        a CUDA graph of forward(x_in, c_img) -> eps, captured once per (shape, strength) and
+        reused across images (set_context / load_step only rewrite buffers the graph reads)."""
+        key = (nb, c, h, w, tuple(float(s) for s in control_scales), self.two_streams)
+        hit = self._graphs.get(key)
+        if hit is not None:
+            return hit
+        x_in = torch.zeros(nb, c, h, w, device=self.dev)
+        c_img = torch.zeros(nb, c, h, w, device=self.dev)
+        eps = torch.empty(nb, c, h, w, device=self.dev)
+        self.forward(x_in, c_img, control_scales, out=eps)        # warm-up: sizes every workspace buffer
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib.launches()
+        with torch.cuda.graph(graph):
+            self.forward(x_in, c_img, control_scales, out=eps)
+        n = lib.launches() - n0
+        lib.count_launch(-n)                                       # capture executes nothing
+        self._graphs[key] = (graph, x_in, c_img, eps, n)
+        return self._graphs[key]
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, c_img: torch.Tensor, control_scales: Sequence[float],

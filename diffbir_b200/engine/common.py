@@ -15,7 +15,7 @@ class Workspace:
     def __init__(self, device):
         self.device = device
         self._bufs: Dict[str, torch.Tensor] = {}
-        self.frozen = False
+        self.on_grow = None      # called before a buffer is (re)allocated: captured graphs hold raw pointers
 
     def get(self, tag: str, shape, dtype, zero: bool = False) -> torch.Tensor:
         n = 1
@@ -24,8 +24,10 @@ class Workspace:
         key = f"{tag}:{dtype}"
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < n:
-            if self.frozen:
-                raise RuntimeError(f"workspace buffer '{tag}' would grow after capture")
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError(f"workspace buffer '{tag}' would be allocated during graph capture")
+            if self.on_grow is not None:
+                self.on_grow()
             buf = (torch.zeros if zero else torch.empty)(max(n, 1), dtype=dtype, device=self.device)
             self._bufs[key] = buf
         return buf[:n].view(*shape)

@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
         ("split_k", C.c_int32), ("reserved1", C.c_int32),
+        ("debug_stamps", C.c_void_p),
     ]
 
 
@@ -122,7 +123,7 @@ ACT = {None: 0, "none": 0, "gelu": 1, "lrelu": 2, "silu": 3}
 def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual=None,
          lda=0, ldb=0, ldo=None, ldr=None, conv=None, act=None, act_param=0.0, alpha=1.0,
          geglu=False, force_bn=0, bias_per_row=False, out2=None, ldo2=None, splitk_ws=None,
-         split_k=0):
+         split_k=0, debug_stamps=None, debug_flags=0):
     """out = residual + alpha * act(A @ B^T + bias + rowvec). conv = (n, h, w, c, ksize)."""
     lib = load()
     g = GemmArgs()
@@ -152,6 +153,8 @@ def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual
         g.splitk_ws = splitk_ws.data_ptr()
         g.splitk_ws_bytes = splitk_ws.numel() * splitk_ws.element_size()
     g.split_k = split_k
+    g.debug_stamps = _ptr(debug_stamps)
+    g.reserved1 = debug_flags
     with _Prof("conv" if conv is not None else "gemm", (M, N, K), 2.0 * M * N * K):
         check(lib.dbir_gemm(C.byref(g), C.c_void_p(stream_ptr())), "dbir_gemm")
     count_launch()

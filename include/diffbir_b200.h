@@ -62,6 +62,7 @@ typedef struct dbir_gemm_args {
   int64_t splitk_ws_bytes;
   int32_t split_k;      /* 0 = auto, 1 = off, n > 1 = force n splits */
   int32_t reserved1;
+  void* debug_stamps;   /* optional int64 [ctas][4] clock64 stamps (start, setup, acc ready, end) */
 } dbir_gemm_args;
 int dbir_gemm(const dbir_gemm_args* args, void* stream);
 

@@ -41,11 +41,15 @@ def test_gemm_plain(L, M, N, K, fbn):
     a, b = rnd(M, K, seed=1).to(dt), rnd(N, K, seed=2, scale=K ** -0.5).to(dt)
     bias, res = rnd(N, seed=3), rnd(M, N, seed=4)
     out = torch.empty(M, N, device="cuda")
-    out16 = torch.empty(M, N, device="cuda", dtype=dt)
-    L.gemm(a, b, out, M=M, N=N, K=K, bias=bias, residual=res, force_bn=fbn, alpha=0.7, out2=out16)
+    out16 = torch.empty(M, N + 8, device="cuda", dtype=dt)
+    L.gemm(a, b, out, M=M, N=N, K=K, bias=bias, residual=res, force_bn=fbn, alpha=0.7)
+    L.gemm(a, b, out16, M=M, N=N, K=K, bias=bias, residual=res, force_bn=fbn, alpha=0.7, ldo=N + 8)
     ref = 0.7 * (a.float() @ b.float().t() + bias) + res
     assert rel_err(out, ref) < 2e-5
-    assert rel_err(out16, ref) < tol16(L)
+    assert rel_err(out16[:, :N], ref) < tol16(L)
+    inplace = res.clone()
+    L.gemm(a, b, inplace, M=M, N=N, K=K, bias=bias, residual=inplace, force_bn=fbn, alpha=0.7)
+    assert torch.equal(inplace, out)
 
 
 def test_gemm_bias_per_row_and_strides(L):
