@@ -512,10 +512,15 @@ TilePlan pick_plan(int m_tiles, int N, int num_kb, int geglu, int forced_bn, int
       if (split_req > 1 && s != split_req) continue;
       const int kbs = (num_kb + s - 1) / s;
       if (static_cast<long long>(kbs) * (s - 1) >= num_kb) continue;   // an empty split
-      const double waves = static_cast<double>((tiles * s + sms - 1) / sms);
-      double cta = 3000.0 + kbs * 3.05 * (128 + bn) + 20.0 * bn;
-      if (s > 1) cta += 15.0 * bn + 6.0 * bn * s;
-      const double cost = waves * cta;
+      const long long ctas = tiles * s;
+      const double waves = static_cast<double>((ctas + sms - 1) / sms);
+      // measured on B200: ~3 cycles per byte-row of L2 feed per k-block, ~2000 cycles per 32-column
+      // epilogue chunk (half hidden when a second CTA shares the SM), ~1500 fixed
+      const double main = kbs * 3.05 * (128 + bn);
+      double epi = 65.0 * bn;
+      if (s > 1) epi += 30.0 * bn + 6.0 * bn * s;
+      const bool shared_sm = ctas > sms && bn <= 160;
+      const double cost = waves * (1500.0 + main + (shared_sm ? 0.5 : 1.0) * epi);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = TilePlan{bn, s, kbs}; }
     }
   }

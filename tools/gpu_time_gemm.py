@@ -37,7 +37,7 @@ def main():
         nout = N // 2 if geglu else N
         out = torch.empty(M, nout, device=dev, dtype=dt if geglu or (kind == "gemm" and N >= 960) else torch.float32)
         res = torch.randn(M, nout, device=dev) if out.dtype == torch.float32 else None
-        fbn = (128 if N >= 10240 else 256) if geglu else 0
+        fbn = 128 if geglu else 0
 
         def call():
             lib.gemm(a, b, out, M=M, N=N, K=K, bias=bias, residual=res, conv=(conv + (3,)) if conv else None,
