@@ -8,8 +8,10 @@
 // QKV projection). One CTA = one (128-query tile, head, batch):
 //   warp 0   TMA producer   (Q once, K/V tiles of 128 keys, 2 stages)
 //   warp 1   MMA issuer     S = Q K^T -> TMEM[0:128), PV -> TMEM[128:192)
-//   warps 2-5 softmax       thread == query row: online softmax in fp32 with exp2,
-//                            P (16-bit) -> swizzled smem, running O kept in registers.
+//   warps 2-5 softmax       thread == query row: the whole 128-wide score row is pulled into
+//                            registers with one TMEM wait, online softmax in fp32 with exp2,
+//                            P (16-bit) -> swizzled smem; O accumulates in TMEM across key tiles
+//                            and is rescaled in place (tcgen05.ld/st) only when a row max moves.
 // Two CTAs are resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax
 // overlaps the other's MMAs.
 #include "common.cuh"
@@ -120,7 +122,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         for (int k = 0; k < TK / 16; ++k)
           umma_f16(tmem_base + TM_O,
                    umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                   umma_desc_sw128(v_addr + k * 16 * 128), idesc_o, k != 0 ? 1u : 0u);
+                   umma_desc_sw128(v_addr + k * 16 * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         umma_commit(&bar->o_full);
         umma_commit(&bar->kv_empty[s]);
       }
@@ -132,9 +134,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     const uint32_t t_o = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TM_O;
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[DH];
-#pragma unroll
-    for (int c = 0; c < DH; ++c) o_acc[c] = 0.f;
     uint8_t* p_row = sP + r * 128;
     const int sw = r & 7;
 
@@ -142,84 +141,89 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       const int valid = min(TK, p.skv - j * TK);
       mbar_wait(&bar->s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < TK; c0 += 32) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(t_s + c0, v);
-        tmem_ld_wait();
+      // whole score row (128 fp32) into registers with a single wait
+      uint32_t s[TK];
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < valid) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+      for (int c0 = 0; c0 < TK; c0 += 32) tmem_ld32(t_s + c0, s + c0);
+      tmem_ld_wait();
+      float m_tile = -INFINITY;
+      if (valid == TK) {
+#pragma unroll
+        for (int i = 0; i < TK; ++i) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < TK; ++i)
+          if (i < valid) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
       }
       const float m_new = fmaxf(m_run, m_tile);
       const float alpha = exp2f((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
-      float l_tile = 0.f;
-      // P(j-1) must have been consumed by PV(j-1) before it is overwritten: o_full(j-1) was
-      // awaited below in the previous iteration.
-#pragma unroll 1
-      for (int c0 = 0; c0 < TK; c0 += 32) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(t_s + c0, v);
-        tmem_ld_wait();
-        float e[32];
+      // PV(j-1) must have retired before P is overwritten and before O is rescaled
+      if (j > 0) {
+        mbar_wait(&bar->o_full, (j - 1) & 1);
+        tc_fence_after();
+        // O (fp32, TMEM) *= alpha for rows whose running max moved; warp-uniform decision because
+        // tcgen05.ld/st are warp-collective
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = exp2f(__uint_as_float(v[i]) * sl2 - mb);
-          e[i] = (c0 + i < valid) ? x : 0.f;
+          for (int c0 = 0; c0 < DH; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(t_o + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(t_o + c0, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      float l_tile = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < TK; c0 += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = exp2f(__uint_as_float(s[c0 + i]) * sl2 - mb);
+          e[i] = (valid == TK || c0 + i < valid) ? x : 0.f;
           l_tile += e[i];
         }
-        // 32 columns = 4 chunks of 16 bytes inside sub-tile c0/64
-        uint8_t* base = p_row + (c0 >> 6) * TILE_BYTES;
-        const int chunk0 = (c0 & 63) >> 3;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint4 t;
-          t.x = pack2(e[ch * 8 + 0], e[ch * 8 + 1]);
-          t.y = pack2(e[ch * 8 + 2], e[ch * 8 + 3]);
-          t.z = pack2(e[ch * 8 + 4], e[ch * 8 + 5]);
-          t.w = pack2(e[ch * 8 + 6], e[ch * 8 + 7]);
-          *reinterpret_cast<uint4*>(base + (((chunk0 + ch) ^ sw) << 4)) = t;
-        }
+        uint4 t;
+        t.x = pack2(e[0], e[1]); t.y = pack2(e[2], e[3]); t.z = pack2(e[4], e[5]); t.w = pack2(e[6], e[7]);
+        // 16-byte chunk (c0 % 64) / 8 of sub-tile c0 / 64, 128-byte swizzle
+        *reinterpret_cast<uint4*>(p_row + (c0 >> 6) * TILE_BYTES + (((((c0 & 63) >> 3)) ^ sw) << 4)) = t;
       }
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&bar->p_full);
-      // O(j) partial
-      mbar_wait(&bar->o_full, j & 1);
-      tc_fence_after();
+    }
+    // epilogue: O / l, 64 x 16-bit = 128 bytes per row
+    mbar_wait(&bar->o_full, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const int qi = q0 + r;
+    const float inv = 1.0f / l_run;
+    op_t* o_ptr = reinterpret_cast<op_t*>(p.out) + (static_cast<long long>(b) * p.sq + qi) * p.ldo + head * DH;
 #pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 32) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(t_o + c0, v);
-        tmem_ld_wait();
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t o[32];
+      __syncwarp();
+      tmem_ld32(t_o + c0, o);
+      tmem_ld_wait();
+      if (qi < p.sq) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = o_acc[c0 + i] * alpha + __uint_as_float(v[i]);
+        for (int c = 0; c < 32; c += 8) {
+          uint4 t;
+          t.x = pack2(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+          t.y = pack2(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+          t.z = pack2(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+          t.w = pack2(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(o_ptr + c0 + c) = t;
+        }
       }
     }
     tc_fence_before();
-    // epilogue: normalise and store 64 x 16-bit = 128 bytes per row
-    const int qi = q0 + r;
-    if (qi < p.sq) {
-      const float inv = 1.0f / l_run;
-      op_t* o = reinterpret_cast<op_t*>(p.out) + (static_cast<long long>(b) * p.sq + qi) * p.ldo + head * DH;
-#pragma unroll
-      for (int c = 0; c < DH; c += 8) {
-        uint4 t;
-        t.x = pack2(o_acc[c] * inv, o_acc[c + 1] * inv);
-        t.y = pack2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
-        t.z = pack2(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
-        t.w = pack2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
-        *reinterpret_cast<uint4*>(o + c) = t;
-      }
-    }
   }
   __syncthreads();
   if (warp == 2) {

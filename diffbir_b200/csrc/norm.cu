@@ -52,10 +52,23 @@ gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
     const int c = cb + lane * 4;
     float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
-      for (int p = p_begin + warp; p < p_end; p += GN_WARPS) {
-        const long long pix = static_cast<long long>(n) * hw + p;
+      // 4 pixels per step, all four loads in flight before the first add (the chunk is sized so a
+      // warp usually owns exactly 4 pixels: one memory latency per slab instead of four)
+      int p = p_begin + warp;
+      for (; p + 3 * GN_WARPS < p_end; p += 4 * GN_WARPS) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = *reinterpret_cast<const float4*>(cat_ptr(s1, s2, c1, c2, static_cast<long long>(n) * hw + p + u * GN_WARPS, c));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sum[0] += v[u].x; sum[1] += v[u].y; sum[2] += v[u].z; sum[3] += v[u].w;
+          sq[0] += v[u].x * v[u].x; sq[1] += v[u].y * v[u].y; sq[2] += v[u].z * v[u].z; sq[3] += v[u].w * v[u].w;
+        }
+      }
+      for (; p < p_end; p += GN_WARPS) {
         // c1, c2 are multiples of 4, so a float4 never straddles the concat boundary
-        const float4 v = *reinterpret_cast<const float4*>(cat_ptr(s1, s2, c1, c2, pix, c));
+        const float4 v = *reinterpret_cast<const float4*>(cat_ptr(s1, s2, c1, c2, static_cast<long long>(n) * hw + p, c));
         sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
         sq[0] += v.x * v.x; sq[1] += v.y * v.y; sq[2] += v.z * v.z; sq[3] += v.w * v.w;
       }
@@ -245,10 +258,12 @@ extern "C" int64_t dbir_gn_workspace_floats(int32_t n, int32_t hw, int32_t c) {
 }
 
 static int gn_chunks(int n, int hw, int* pix_per_chunk) {
-  // aim for >= 2 waves of CTAs, at least 8 pixels (one per warp) per chunk
+  // 32 pixels per chunk (4 per warp, loaded together) unless that would leave the GPU under-filled
+  // or exceed the partial buffer; at least 8 pixels (one per warp) per chunk
   const int target = 2 * dbir_sm_count();
   int chunks = (target + n - 1) / n;
   int ppc = (hw + chunks - 1) / chunks;
+  if (ppc < 32 && hw * static_cast<long long>(n) >= 32LL * dbir_sm_count()) ppc = 32;
   if (ppc < 8) ppc = 8;
   chunks = (hw + ppc - 1) / ppc;
   if (chunks > 1024) { chunks = 1024; ppc = (hw + chunks - 1) / chunks; chunks = (hw + ppc - 1) / ppc; }
