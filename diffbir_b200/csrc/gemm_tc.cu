@@ -56,6 +56,10 @@ struct GemmParams {
   float* ws;
   unsigned int* tickets;
   long long* dbg;          // optional per-CTA clock64 stamps [ctas][4]: start, setup done, acc ready, end
+  // fused GroupNorm statistics of the OUTPUT tensor: per (image, 32-row slot, channel) sum / sum of
+  // squares over the warp's rows -> stats[(img * nslots + slot) * N + col][2] (fp32 outputs only)
+  float* stats;
+  int stats_nslots, stats_rows_per_img, stats_slots_x;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float prm) {
@@ -94,6 +98,7 @@ struct EpiCtx {
   uint32_t res_bar;        // shared address of this warp's two residual-load mbarriers
   int row0;                // plain mode: first global row of this warp
   int x, y, n;             // conv mode: origin of this warp's sub-box
+  long long stats_base;    // element offset of this warp's (image, slot) row in the stats buffer, < 0: none
   __device__ __forceinline__ uint32_t out_buf(int b) const { return epi_base + b * EPI_TILE_BYTES; }
   __device__ __forceinline__ uint32_t res_buf(int b) const { return epi_base + (2 + b) * EPI_TILE_BYTES; }
   __device__ __forceinline__ uint32_t bar(int b) const { return res_bar + b * 8; }
@@ -212,6 +217,21 @@ __device__ __forceinline__ void finish_chunk(const GemmParams& p, EpiCtx& e, flo
   }
   fence_proxy_async_smem();
   __syncwarp();
+  if (p.stats && e.stats_base >= 0 && p.out_kind == 0) {
+    // column sums over the warp's valid rows, read back from the staged tile (lane == column)
+    const uint32_t valid = __ballot_sync(0xffffffffu, out_row >= 0);
+    float sa = 0.f, sb = 0.f;
+    const uint32_t col_off = static_cast<uint32_t>(lane & 3) * 4;
+    const int chunk = lane >> 2;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float x;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(e.out_buf(b) + i * 128 + (((chunk ^ (i & 7))) << 4) + col_off) : "memory");
+      if ((valid >> i) & 1u) { sa += x; sb += x * x; }
+    }
+    if (lane < ncols)
+      *reinterpret_cast<float2*>(p.stats + (e.stats_base + gc0 + lane) * 2) = make_float2(sa, sb);
+  }
   if (lane == 0) {
     if (p.mode == 0) tma_store_2d(e.tm_out, e.out_buf(b), gc0, e.row0);
     else tma_store_4d(e.tm_out, e.out_buf(b), gc0, e.x, e.y, e.n);
@@ -220,7 +240,7 @@ __device__ __forceinline__ void finish_chunk(const GemmParams& p, EpiCtx& e, flo
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, BN <= 160 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
                const GemmParams p) {
@@ -342,6 +362,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       e.x = x0 + r0 % p.bw;
       e.y = y0 + (r0 / p.bw) % p.bh;
       e.n = n0 + r0 / (p.bw * p.bh);
+    }
+    e.stats_base = -1;
+    if (p.stats) {
+      if (p.mode == 0) {
+        const int img = e.row0 / p.stats_rows_per_img, slot = (e.row0 % p.stats_rows_per_img) / 32;
+        if (e.row0 < p.M) e.stats_base = (static_cast<long long>(img) * p.stats_nslots + slot) * p.N;
+      } else if (e.x < p.W && e.y < p.H && e.n < p.NI) {
+        const int slot = (e.y / p.wbh) * p.stats_slots_x + e.x / p.wbw;
+        e.stats_base = (static_cast<long long>(e.n) * p.stats_nslots + slot) * p.N;
+      }
     }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
@@ -624,6 +654,20 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
     }
   }
 
+  if (a->gn_partials) {
+    DBIR_REQUIRE(a->out_kind == 0 && !a->geglu, "dbir_gemm: gn_partials needs an fp32, non-GEGLU output");
+    p.stats = reinterpret_cast<float*>(a->gn_partials);
+    if (a->a_mode == 0) {
+      DBIR_REQUIRE(a->gn_rows_per_img > 0 && a->gn_rows_per_img % 32 == 0 && a->M % a->gn_rows_per_img == 0,
+                   "dbir_gemm: gn_partials in matrix mode needs rows-per-image that is a multiple of 32");
+      p.stats_rows_per_img = a->gn_rows_per_img;
+      p.stats_nslots = a->gn_rows_per_img / 32;
+    } else {
+      DBIR_REQUIRE(p.bw * p.bh >= 32, "dbir_gemm: gn_partials needs images of at least 32 pixels");
+      p.stats_slots_x = (p.W + p.wbw - 1) / p.wbw;
+      p.stats_nslots = p.stats_slots_x * ((p.H + p.wbh - 1) / p.wbh);
+    }
+  }
   constexpr long long TICKET_FLOATS = 16384;
   const long long ws_floats = a->splitk_ws ? a->splitk_ws_bytes / 4 - TICKET_FLOATS : 0;
   const TilePlan plan = pick_plan(m_tiles, a->N, p.num_kb, a->geglu, a->force_bn, a->split_k, ws_floats);
@@ -652,4 +696,18 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
       dbir_set_error("dbir_gemm: unsupported tile width %d", bn);
       return -2;
   }
+}
+
+extern "C" int32_t dbir_gemm_gn_slots(int32_t conv_h, int32_t conv_w, int32_t rows_per_img) {
+  if (conv_h > 0 && conv_w > 0) {
+    int bw = 1;
+    while (bw < conv_w && bw < 128) bw <<= 1;
+    int bh = 1;
+    while (bh < conv_h && bw * bh < 128) bh <<= 1;
+    const int wbw = bw < 32 ? bw : 32;
+    const int wbh = bh < 32 / wbw ? bh : 32 / wbw;
+    if (wbw * wbh < 32) return -1;
+    return ((conv_w + wbw - 1) / wbw) * ((conv_h + wbh - 1) / wbh);
+  }
+  return rows_per_img > 0 && rows_per_img % 32 == 0 ? rows_per_img / 32 : -1;
 }

@@ -131,6 +131,53 @@ gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
   }
 }
 
+// Finalisation of statistics whose partial sums were emitted by the producing GEMM epilogues
+// (dbir_gemm gn_partials): grid (32 groups, N), fixed-order fp64 combine.
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float* __restrict__ p2,
+                   int slots2, int c2, int hw, float eps, float* __restrict__ stats) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = c1 + c2, cpg = C / 32;
+  const int ch0 = g * cpg, ch1 = ch0 + cpg;
+  double a = 0.0, b = 0.0;
+  // source 1: channels [ch0, ch1) ∩ [0, c1)
+  {
+    const int lo = min(ch0, c1), hi = min(ch1, c1), w = hi - lo;
+    const int total = w * slots1;
+    const float* base = p1 + static_cast<long long>(n) * slots1 * c1 * 2;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int sl = i / w, cc = lo + i % w;
+      const float2 v = *reinterpret_cast<const float2*>(base + (static_cast<long long>(sl) * c1 + cc) * 2);
+      a += v.x; b += v.y;
+    }
+  }
+  if (c2 > 0) {
+    const int lo = max(ch0, c1) - c1, hi = max(ch1, c1) - c1, w = hi - lo;
+    const int total = w * slots2;
+    const float* base = p2 + static_cast<long long>(n) * slots2 * c2 * 2;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int sl = i / w, cc = lo + i % w;
+      const float2 v = *reinterpret_cast<const float2*>(base + (static_cast<long long>(sl) * c2 + cc) * 2);
+      a += v.x; b += v.y;
+    }
+  }
+  __shared__ double sa[128], sb[128];
+  sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double cnt = static_cast<double>(hw) * cpg;
+    const double mean = sa[0] / cnt;
+    double var = sb[0] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(n * 32 + g) * 2 + 0] = static_cast<float>(mean);
+    stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
 // Stage 2: y = silu?(x * a[c] + b[c]) -> op16, optional 2x nearest upsample, optional raw copy.
 // grid = (pixel chunks, N)
 __global__ void __launch_bounds__(256)
@@ -284,6 +331,17 @@ extern "C" int dbir_gn_stats(const float* src1, const float* src2, int32_t c1, i
   float* partial = workspace + 64 + ((n + 3) / 4) * 4;
   gn_stats_kernel<<<dim3(chunks, n), GN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src1, src2, c1, c2, hw, ppc, partial, tickets, stats, eps);
+  DBIR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dbir_gn_finalize(const float* partials1, int32_t slots1, int32_t c1, const float* partials2,
+                                int32_t slots2, int32_t c2, int32_t n, int32_t hw, float eps, float* stats,
+                                void* stream) {
+  DBIR_REQUIRE(partials1 && stats && slots1 > 0 && (c1 + c2) % 32 == 0, "dbir_gn_finalize: bad args");
+  DBIR_REQUIRE(c2 == 0 || (partials2 && slots2 > 0), "dbir_gn_finalize: second source missing");
+  gn_finalize_kernel<<<dim3(32, n), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partials1, slots1, c1, partials2, slots2, c2, hw, eps, stats);
   DBIR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -144,6 +144,8 @@ class CldmEngine:
         self.two_streams = True          # ControlNet || UNet encoder
         self._side = None
         self._ts_key = None
+        self._part = {}                  # fp32 activation data_ptr -> (GN partial-sum buffer, slots)
+        self.fuse_gn_stats = True
         self.emb_cur = None
         self._graphs = {}                # (shape, scales) -> (CUDAGraph, x_in, c_img, eps, launches)
         self.ws.on_grow = self._graphs.clear
@@ -223,12 +225,32 @@ class CldmEngine:
 
     # ------------------------------------------------------------------ blocks
     def _gn(self, tag, src1, src2, c1, c2, nb, h, w, eps, gamma, beta, out16, silu, out_raw=None):
+        """GroupNorm(+SiLU) of the virtual concat [src1 | src2] -> 16-bit operand. Statistics come
+        from the partial sums the producing GEMM epilogues emitted (dbir_gn_finalize); tensors
+        without partials (the stem conv output) take the stand-alone statistics kernel."""
         ws = self.ws
         stats = ws.get(tag + ":gn_stats", (nb * 64,), torch.float32)
-        wsp = ws.get(tag + ":gn_ws", (lib.gn_workspace_floats(nb, h * w, c1 + c2),), torch.float32, zero=True)
-        lib.gn_stats(src1, src2, c1, c2, nb, h * w, eps, stats, wsp)
+        p1 = self._part.get(src1.data_ptr())
+        p2 = self._part.get(src2.data_ptr()) if src2 is not None else None
+        if self.fuse_gn_stats and p1 is not None and (src2 is None or p2 is not None):
+            lib.gn_finalize(p1[0], p1[1], c1, p2[0] if p2 else None, p2[1] if p2 else 0, c2, nb, h * w, eps, stats)
+        else:
+            wsp = ws.get(tag + ":gn_ws", (lib.gn_workspace_floats(nb, h * w, c1 + c2),), torch.float32, zero=True)
+            lib.gn_stats(src1, src2, c1, c2, nb, h * w, eps, stats, wsp)
         lib.gn_apply(src1, src2, c1, c2, nb, h, w, stats, gamma, beta, out16, norm=True, silu=silu,
                      out_raw=out_raw)
+
+    def _stats_kw(self, out: torch.Tensor, nb: int, n_cols: int, conv_hw=None, rows_per_img: int = 0) -> dict:
+        """kwargs that make dbir_gemm emit GroupNorm partial sums for its output tensor `out`."""
+        if not self.fuse_gn_stats:
+            return {}
+        slots = lib.gemm_gn_slots(*conv_hw) if conv_hw else lib.gemm_gn_slots(0, 0, rows_per_img)
+        if slots <= 0:
+            self._part.pop(out.data_ptr(), None)
+            return {}
+        buf = self.ws.get(f"part:{out.data_ptr()}", (nb * slots * n_cols * 2,), torch.float32)
+        self._part[out.data_ptr()] = (buf, slots)
+        return dict(gn_partials=buf) if conv_hw else dict(gn_partials=buf, gn_rows_per_img=rows_per_img)
 
     def _res(self, net: _Net, tag: str, l: arch.Layer, src1, src2, c1, c2, nb, h, w, out):
         """ResBlock._forward (unet.py:203-223): out may alias src1 when c2 == 0."""
@@ -240,7 +262,8 @@ class CldmEngine:
                  W[p + "in_layers.0.bias"], a16, True, out_raw=raw16)
         h1 = ws.get(tag + ":res_h1", (M, cout), torch.float32)
         self._gemm(tag, a16, W[p + "conv1.w"], h1, M=M, N=cout, K=9 * cin, bias=W[p + "conv1.b"],
-                 rowvec=self._emb(tag, l, nb), conv=(nb, h, w, cin, 3))
+                   rowvec=self._emb(tag, l, nb), conv=(nb, h, w, cin, 3),
+                   **self._stats_kw(h1, nb, cout, conv_hw=(h, w)))
         b16 = ws.get(tag + ":res_b16", (M, cout), self.op_dtype)
         self._gn(tag, h1, None, cout, 0, nb, h, w, 1e-5, W[p + "out_layers.0.weight"],
                  W[p + "out_layers.0.bias"], b16, True)
@@ -251,7 +274,7 @@ class CldmEngine:
         else:
             res = src1
         self._gemm(tag, b16, W[p + "conv2.w"], out, M=M, N=cout, K=9 * cout, bias=W[p + "conv2.b"],
-                 residual=res, conv=(nb, h, w, cout, 3))
+                   residual=res, conv=(nb, h, w, cout, 3), **self._stats_kw(out, nb, cout, conv_hw=(h, w)))
 
     def _attn(self, net: _Net, tag: str, l: arch.Layer, x, nb, h, w):
         """SpatialTransformer.forward, in place on x (fp32 NHWC [nb,h,w,C]) — attention.py:334-353."""
@@ -285,21 +308,23 @@ class CldmEngine:
         self._gemm(tag, a16, W[q + "ff1.w"], ffh, M=M, N=8 * c, K=c, bias=W[q + "ff1.b"], geglu=True,
                  force_bn=geglu_tile(c))
         self._gemm(tag, ffh, W[q + "ff2.w"], a16, M=M, N=c, K=4 * c, bias=W[q + "ff2.b"], residual=t)
-        self._gemm(tag, a16, W[p + "proj_out.w"], x, M=M, N=c, K=c, bias=W[p + "proj_out.b"], residual=x)
+        self._gemm(tag, a16, W[p + "proj_out.w"], x, M=M, N=c, K=c, bias=W[p + "proj_out.b"], residual=x,
+                   **self._stats_kw(x, nb, c, rows_per_img=hw))
 
     def _down(self, net: _Net, tag: str, l: arch.Layer, x, nb, h, w, out):
         c, ho, wo = l.cin, h // 2, w // 2
         col = self.ws.get(tag + ":down_col", (nb * ho * wo, 9 * c), self.op_dtype)
         lib.im2col_s2(x, nb, h, w, c, 1, col)
         self._gemm(tag, col, net.w[l.prefix + "w"], out, M=nb * ho * wo, N=l.cout, K=9 * c,
-                 bias=net.w[l.prefix + "b"])
+                   bias=net.w[l.prefix + "b"], **self._stats_kw(out, nb, l.cout, rows_per_img=ho * wo))
 
     def _up(self, net: _Net, tag: str, l: arch.Layer, x, nb, h, w, out):
         c = l.cin
         up16 = self.ws.get("up_a16", (nb * 4 * h * w, c), self.op_dtype)
         lib.gn_apply(x, None, c, 0, nb, h, w, None, None, None, up16, norm=False, silu=False, upsample=2)
         self._gemm(tag, up16, net.w[l.prefix + "w"], out, M=nb * 4 * h * w, N=l.cout, K=9 * c,
-                 bias=net.w[l.prefix + "b"], conv=(nb, 2 * h, 2 * w, c, 3))
+                   bias=net.w[l.prefix + "b"], conv=(nb, 2 * h, 2 * w, c, 3),
+                   **self._stats_kw(out, nb, l.cout, conv_hw=(2 * h, 2 * w)))
 
     def _encoder(self, net: _Net, tag: str, x_in, hint, nb, h, w, keep: bool):
         """Input blocks + middle. Returns (list of (tensor, c, h, w) per input block, middle)."""
@@ -314,6 +339,7 @@ class CldmEngine:
                     c2 = hint.shape[1] if hint is not None else 0
                     lib.conv3x3_small_cin(x_in, hint, c1, c2, nb, h, w, net.w[l.prefix + "w"],
                                           net.w[l.prefix + "b"], l.cout, o)
+                    self._part.pop(o.data_ptr(), None)      # written without GEMM partials
                     cur, cc = o, l.cout
                 elif l.kind == "res":
                     o = ws.get(f"{tag}_hs{bi}", (nb * ch * cw, l.cout), torch.float32)
@@ -392,12 +418,12 @@ class CldmEngine:
             lib.gn_apply(t, None, c, 0, nb, th, tw, None, None, None, a16, norm=False, silu=False)
             tgt = hs[i][0]
             self._gemm("u", a16, Cn.w[f"zero_convs.{i}.w"], tgt, M=M, N=c, K=c, bias=Cn.w[f"zero_convs.{i}.b"],
-                     alpha=float(control_scales[i]), residual=tgt)
+                       alpha=float(control_scales[i]), residual=tgt, **self._stats_kw(tgt, nb, c, rows_per_img=th * tw))
         M = nb * cmh * cmw
         a16 = ws.get("zc_a16", (M, cmc), self.op_dtype)
         lib.gn_apply(cmid, None, cmc, 0, nb, cmh, cmw, None, None, None, a16, norm=False, silu=False)
         self._gemm("u", a16, Cn.w["middle_block_out.w"], mid, M=M, N=cmc, K=cmc, bias=Cn.w["middle_block_out.b"],
-                 alpha=float(control_scales[len(chs)]), residual=mid)
+                   alpha=float(control_scales[len(chs)]), residual=mid, **self._stats_kw(mid, nb, cmc, rows_per_img=cmh * cmw))
         # 3. UNet decoder over virtual concats
         cur, cc, ch, cw = mid, mc_, mh, mw
         stack = list(hs)

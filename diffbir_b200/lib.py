@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
         ("split_k", C.c_int32), ("reserved1", C.c_int32),
         ("debug_stamps", C.c_void_p),
+        ("gn_partials", C.c_void_p), ("gn_rows_per_img", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -123,7 +124,7 @@ ACT = {None: 0, "none": 0, "gelu": 1, "lrelu": 2, "silu": 3}
 def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual=None,
          lda=0, ldb=0, ldo=None, ldr=None, conv=None, act=None, act_param=0.0, alpha=1.0,
          geglu=False, force_bn=0, bias_per_row=False, out2=None, ldo2=None, splitk_ws=None,
-         split_k=0, debug_stamps=None, debug_flags=0):
+         split_k=0, debug_stamps=None, gn_partials=None, gn_rows_per_img=0):
     """out = residual + alpha * act(A @ B^T + bias + rowvec). conv = (n, h, w, c, ksize)."""
     lib = load()
     g = GemmArgs()
@@ -154,7 +155,8 @@ def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual
         g.splitk_ws_bytes = splitk_ws.numel() * splitk_ws.element_size()
     g.split_k = split_k
     g.debug_stamps = _ptr(debug_stamps)
-    g.reserved1 = debug_flags
+    g.gn_partials = _ptr(gn_partials)
+    g.gn_rows_per_img = gn_rows_per_img
     with _Prof("conv" if conv is not None else "gemm", (M, N, K), 2.0 * M * N * K):
         check(lib.dbir_gemm(C.byref(g), C.c_void_p(stream_ptr())), "dbir_gemm")
     count_launch()
@@ -181,6 +183,16 @@ def gn_workspace_floats(n, hw, c) -> int:
     lib = load()
     lib.dbir_gn_workspace_floats.restype = C.c_int64
     return int(lib.dbir_gn_workspace_floats(n, hw, c))
+
+
+def gemm_gn_slots(conv_h=0, conv_w=0, rows_per_img=0) -> int:
+    return int(load().dbir_gemm_gn_slots(conv_h, conv_w, rows_per_img))
+
+
+def gn_finalize(p1, slots1, c1, p2, slots2, c2, n, hw, eps, stats):
+    check(load().dbir_gn_finalize(_fp(p1), slots1, c1, _fp(p2), slots2, c2, n, hw, C.c_float(eps), _fp(stats),
+                                  _sp()), "dbir_gn_finalize")
+    count_launch()
 
 
 def gn_stats(src1, src2, c1, c2, n, hw, eps, stats, workspace):

@@ -62,8 +62,14 @@ typedef struct dbir_gemm_args {
   int64_t splitk_ws_bytes;
   int32_t split_k;      /* 0 = auto, 1 = off, n > 1 = force n splits */
   int32_t reserved1;
-  void* debug_stamps;   /* optional int64 [ctas][4] clock64 stamps (start, setup, acc ready, end) */
+  void* debug_stamps;   /* optional int64 [ctas][8] clock64 stamps (start, setup, acc ready, end) */
+  void* gn_partials;    /* optional fp32 [img][dbir_gemm_gn_slots()][N][2]: per 32-row-slot column sums and
+                           sums of squares of the OUTPUT (fused GroupNorm statistics; see dbir_gn_finalize) */
+  int32_t gn_rows_per_img; /* matrix mode only: rows per image (multiple of 32); conv mode uses img_h*img_w */
+  int32_t reserved2;
 } dbir_gemm_args;
+/* Number of 32-row slots per image dbir_gemm writes into gn_partials (conv: h, w > 0; matrix: rows_per_img). */
+int32_t dbir_gemm_gn_slots(int32_t conv_h, int32_t conv_w, int32_t rows_per_img);
 int dbir_gemm(const dbir_gemm_args* args, void* stream);
 
 /* ---- flash attention, head_dim 64 (tcgen05) ------------------------------------------
@@ -89,6 +95,12 @@ int dbir_attention(const void* q, const void* k, const void* v, void* out, int32
  * swinir.py:208,214,722,783; eps 1e-5); columns [c, ldo) are zero-filled.
  */
 int64_t dbir_gn_workspace_floats(int32_t n, int32_t hw, int32_t c);
+/* Per-(image, group) mean / rstd from the partial sums dbir_gemm emitted while writing the tensor(s)
+ * (virtual concat of two tensors: partials1 [n][slots1][c1][2], partials2 [n][slots2][c2][2] or NULL).
+ * hw = pixels per image. Deterministic (fixed summation order, fp64 combine). */
+int dbir_gn_finalize(const float* partials1, int32_t slots1, int32_t c1, const float* partials2,
+                     int32_t slots2, int32_t c2, int32_t n, int32_t hw, float eps, float* stats,
+                     void* stream);
 int dbir_gn_stats(const float* src1, const float* src2, int32_t c1, int32_t c2, int32_t n,
                   int32_t hw, float eps, float* stats, float* workspace, void* stream);
 int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, int32_t c2, int32_t n,

@@ -278,3 +278,41 @@ def test_gemm_split_k_deterministic(L, n, h, w, cin, cout, split):
     assert rel_err(outs[0], ref) < 3e-5
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert (ws[:16384] == 0).all()
+
+
+@pytest.mark.parametrize("n,h,w,c1,c2", [(2, 64, 64, 320, 0), (2, 16, 16, 1280, 640), (2, 8, 8, 1280, 1280),
+                                          (1, 40, 72, 128, 64), (3, 8, 16, 64, 0)])
+def test_fused_groupnorm_statistics(L, n, h, w, c1, c2):
+    """GN statistics from the partial sums emitted by the producing GEMM epilogues (conv mode for
+    source 1, matrix mode for source 2) == statistics of the stored tensors."""
+    dt = L.operand_dtype()
+    hw = h * w
+    outs, parts = [], []
+    for idx, c in enumerate([c1, c2]):
+        if c == 0:
+            outs.append(None); parts.append((None, 0)); continue
+        cin = 64
+        x = rnd(n, h, w, cin, seed=10 + idx).to(dt)
+        res = rnd(n * hw, c, seed=20 + idx) * 2 + 0.3
+        out = torch.empty(n * hw, c, device="cuda")
+        if idx == 0:
+            wt = rnd(c, 9 * cin, seed=30, scale=0.05).to(dt)
+            slots = L.gemm_gn_slots(h, w)
+            part = torch.zeros(n * slots * c * 2, device="cuda")
+            L.gemm(x, wt, out, M=n * hw, N=c, K=9 * cin, residual=res, conv=(n, h, w, cin, 3), gn_partials=part)
+        else:
+            wt = rnd(c, cin, seed=31, scale=0.1).to(dt)
+            slots = L.gemm_gn_slots(0, 0, hw)
+            part = torch.zeros(n * slots * c * 2, device="cuda")
+            L.gemm(x.view(n * hw, cin), wt, out, M=n * hw, N=c, K=cin, residual=res, gn_partials=part, gn_rows_per_img=hw)
+        assert slots > 0
+        outs.append(out); parts.append((part, slots))
+    stats = torch.empty(n * 64, device="cuda")
+    L.gn_finalize(parts[0][0], parts[0][1], c1, parts[1][0], parts[1][1], c2, n, hw, 1e-5, stats)
+    full = outs[0].view(n, hw, c1) if c2 == 0 else torch.cat([outs[0].view(n, hw, c1), outs[1].view(n, hw, c2)], -1)
+    c = c1 + c2
+    g = full.view(n, hw, 32, c // 32).permute(0, 2, 1, 3).reshape(n, 32, -1).double()
+    mean, var = g.mean(-1), g.var(-1, unbiased=False)
+    st = stats.view(n, 32, 2)
+    assert (st[..., 0].double() - mean).abs().max() < 1e-4 * (mean.abs().max() + 1)
+    assert ((st[..., 1].double() - 1 / (var + 1e-5).sqrt()).abs() / (1 / (var + 1e-5).sqrt())).max() < 1e-4
