@@ -1,5 +1,5 @@
-"""-m gpu, >= 2 GPUs: tiled sampling sharded over NCCL ranks == single-rank tiled sampling,
-bit for bit (tools/run_tiled_multi.py under torchrun)."""
+"""-m gpu, >= 2 GPUs: tiled sampling sharded over NCCL ranks matches single-rank tiled sampling to
+rounding level and every rank holds the bit-identical latent (tools/run_tiled_multi.py under torchrun)."""
 import subprocess
 import sys
 from pathlib import Path
@@ -19,5 +19,7 @@ def test_sharded_tiles_bit_identical():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                         "--master-addr", "127.0.0.1", "--master-port", "29531", str(ROOT / "tools" / "run_tiled_multi.py")],
                        capture_output=True, text=True, timeout=900)
-    print(r.stdout[-2000:], r.stderr[-2000:])
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / "tiled_multi.log").write_text(r.stdout + "\n" + r.stderr)
     assert r.returncode == 0

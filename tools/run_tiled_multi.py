@@ -37,12 +37,18 @@ def main():
         torch.manual_seed(231)
         z_single = smp.sample(cl, dev, 4, (1, 4, L, L), cond, unc, 4.0, tiled=True, tile_size=64, tile_stride=32, x_T=xT)
         same = torch.equal(z_multi, z_single)
+        # The per-rank batch differs from the single-rank batch, so dbir_gemm may pick another tile /
+        # split-K plan (different fp32 summation order): compare to rounding level, and require the
+        # replicated state to be bit-identical across ranks (they blend the same gathered tiles).
+        rel = ((z_multi - z_single).abs().max() / z_single.abs().max()).item()
+        close = rel < 2e-3
         allz = [torch.empty_like(z_multi) for _ in range(dist.get_world_size())]
         dist.all_gather(allz, z_multi)
         same_ranks = all(torch.equal(allz[0], t) for t in allz)
         if rank == 0:
-            print(f"{name}: sharded == single-rank: {same}; all ranks identical: {same_ranks}; |z| {z_multi.abs().mean():.4f}")
-        ok = ok and same and same_ranks
+            print(f"{name}: sharded vs single-rank: bit-equal {same}, max rel diff {rel:.2e}; all ranks identical: {same_ranks}; "
+                  f"|z| {z_multi.abs().mean():.4f}", flush=True)
+        ok = ok and close and same_ranks
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
