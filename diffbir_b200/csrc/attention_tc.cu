@@ -82,6 +82,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bar->tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -265,7 +267,7 @@ extern "C" int dbir_attention(const void* q, const void* k, const void* v, void*
     configured = true;
   }
   dim3 grid((sq + TQ - 1) / TQ, heads, batch);
-  attn_fwd_kernel<<<grid, 192, ATTN_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mq, mk, mv, p);
-  DBIR_CHECK_CUDA(cudaGetLastError());
+  DBIR_CHECK_CUDA(dbir_launch(attn_fwd_kernel, grid, dim3(192), ATTN_SMEM, reinterpret_cast<cudaStream_t>(stream),
+                              mq, mk, mv, p));
   return 0;
 }

@@ -82,6 +82,33 @@ extern "C" int dbir_sm_count(void);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): kernels of the step loop are launched with the
+// programmatic-stream-serialization attribute; each one calls pdl_trigger() as soon as its CTA is
+// set up (lets the NEXT kernel's CTAs be scheduled and run their prologue: barrier init, TMEM
+// alloc, descriptor prefetch) and pdl_wait() before touching memory written by its predecessors
+// (griddepcontrol.wait returns when all prerequisite grids completed and flushed). Hides the
+// ~2.5 us kernel-to-kernel latency of the ~600 dependent kernels per forward. DBIR_PDL=0 disables.
+// ---------------------------------------------------------------------------
+extern "C" int dbir_pdl_enabled(void);
+template <typename... KArgs, typename... Args>
+inline cudaError_t dbir_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                               cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dbir_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
 // Device helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -17,6 +17,8 @@ conv3x3_small_cin_kernel(const float* __restrict__ in1, const float* __restrict_
                          int n, int h, int w, const float* __restrict__ wt,
                          const float* __restrict__ bias, int cout, float* __restrict__ out,
                          float in_scale, float in_shift) {
+  pdl_trigger();
+  pdl_wait();
   const int cin = c1 + c2;
   const int cv = cout / 4;
   const long long total = static_cast<long long>(n) * h * w * cv;
@@ -54,6 +56,8 @@ conv3x3_small_cout_kernel(const op_t* __restrict__ in, int n, int h, int w, int 
                           const float* __restrict__ wt, const float* __restrict__ bias,
                           float post_scale, const float* __restrict__ post_shift,
                           float* __restrict__ out, int out_nchw) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -109,6 +113,8 @@ conv3x3_small_cout_kernel(const op_t* __restrict__ in, int n, int h, int w, int 
 __global__ void __launch_bounds__(256)
 im2col_s2_kernel(const float* __restrict__ in, int n, int h, int w, int c, int ho, int wo,
                  int pad_lo, op_t* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = c / 4;
   const long long total = static_cast<long long>(n) * ho * wo * 9 * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -381,9 +387,8 @@ extern "C" int dbir_conv3x3_small_cin(const float* in1, const float* in2, int32_
   DBIR_REQUIRE(in1 && weight_kc && bias && out_nhwc, "dbir_conv3x3_small_cin: null pointer");
   DBIR_REQUIRE(c1 + c2 <= 16 && cout % 4 == 0, "dbir_conv3x3_small_cin: Cin<=16, Cout%%4==0");
   const long long total = static_cast<long long>(n) * h * w * (cout / 4);
-  conv3x3_small_cin_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(
-      in1, in2, c1, c2, n, h, w, weight_kc, bias, cout, out_nhwc, in_scale, in_shift);
-  DBIR_CHECK_CUDA(cudaGetLastError());
+  DBIR_CHECK_CUDA(dbir_launch(conv3x3_small_cin_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), in1, in2, c1,
+                              c2, n, h, w, weight_kc, bias, cout, out_nhwc, in_scale, in_shift));
   return 0;
 }
 
@@ -397,8 +402,8 @@ extern "C" int dbir_conv3x3_small_cout(const void* in_nhwc, int32_t n, int32_t h
   const int grid = grid_for(npix * 32);
   const op_t* in = reinterpret_cast<const op_t*>(in_nhwc);
 #define LAUNCH_SC(C)                                                                              \
-  conv3x3_small_cout_kernel<C><<<grid, 256, 0, ST(stream)>>>(in, n, h, w, cin, weight, bias,      \
-                                                              post_scale, post_shift, out, out_nchw)
+  DBIR_CHECK_CUDA(dbir_launch(conv3x3_small_cout_kernel<C>, dim3(grid), dim3(256), 0, ST(stream), in, n, h, w, cin, \
+                              weight, bias, post_scale, post_shift, out, out_nchw))
   switch (cout) {
     case 3: LAUNCH_SC(3); break;
     case 4: LAUNCH_SC(4); break;
@@ -416,9 +421,8 @@ extern "C" int dbir_im2col_s2(const float* in_nhwc, int32_t n, int32_t h, int32_
   const int ho = pad_lo ? (h + 2 - 3) / 2 + 1 : (h + 1 - 3) / 2 + 1;
   const int wo = pad_lo ? (w + 2 - 3) / 2 + 1 : (w + 1 - 3) / 2 + 1;
   const long long total = static_cast<long long>(n) * ho * wo * 9 * (c / 4);
-  im2col_s2_kernel<<<grid_for(total), 256, 0, ST(stream)>>>(in_nhwc, n, h, w, c, ho, wo, pad_lo,
-                                                            reinterpret_cast<op_t*>(out));
-  DBIR_CHECK_CUDA(cudaGetLastError());
+  DBIR_CHECK_CUDA(dbir_launch(im2col_s2_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), in_nhwc, n, h, w, c,
+                              ho, wo, pad_lo, reinterpret_cast<op_t*>(out)));
   return 0;
 }
 

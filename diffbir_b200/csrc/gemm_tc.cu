@@ -295,6 +295,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();        // the next kernel may start its prologue
+  pdl_wait();           // A operand / residual come from predecessor kernels
   if (p.dbg) t_setup = clock64();
 
   if (warp == 0) {
@@ -509,8 +511,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, 
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  gemm_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ta, tb, to, tr, p);
-  DBIR_CHECK_CUDA(cudaGetLastError());
+  DBIR_CHECK_CUDA(dbir_launch(gemm_tc_kernel<BN, STAGES>, grid, dim3(192), smem, st, ta, tb, to, tr, p));
   return 0;
 }
 

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int c1, int c2,
                 int hw, int pix_per_chunk, float* __restrict__ partial,
                 unsigned int* __restrict__ tickets, float* __restrict__ stats, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int C = c1 + c2;
   const int cpg = C / 32;
   const int n = blockIdx.y;
@@ -136,6 +138,8 @@ gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
 __global__ void __launch_bounds__(128)
 gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float* __restrict__ p2,
                    int slots2, int c2, int hw, float eps, float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   const int g = blockIdx.x, n = blockIdx.y;
   const int C = c1 + c2, cpg = C / 32;
   const int ch0 = g * cpg, ch1 = ch0 + cpg;
@@ -186,6 +190,8 @@ gn_apply_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
                 const float* __restrict__ beta, int do_norm, int do_silu, int up,
                 op_t* __restrict__ out, op_t* __restrict__ out_raw, int pix_per_cta) {
   extern __shared__ float s_ab[];   // [C][2]
+  pdl_trigger();
+  pdl_wait();
   const int C = c1 + c2;
   const int n = blockIdx.y;
   const int hw = h * w;
@@ -244,6 +250,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  void* __restrict__ out_v, long long ldo) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -329,9 +337,9 @@ extern "C" int dbir_gn_stats(const float* src1, const float* src2, int32_t c1, i
   const int chunks = gn_chunks(n, hw, &ppc);
   unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
   float* partial = workspace + 64 + ((n + 3) / 4) * 4;
-  gn_stats_kernel<<<dim3(chunks, n), GN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src1, src2, c1, c2, hw, ppc, partial, tickets, stats, eps);
-  DBIR_CHECK_CUDA(cudaGetLastError());
+  DBIR_CHECK_CUDA(dbir_launch(gn_stats_kernel, dim3(chunks, n), dim3(GN_THREADS), 0,
+                              reinterpret_cast<cudaStream_t>(stream), src1, src2, c1, c2, hw, ppc, partial, tickets,
+                              stats, eps));
   return 0;
 }
 
@@ -340,9 +348,8 @@ extern "C" int dbir_gn_finalize(const float* partials1, int32_t slots1, int32_t 
                                 void* stream) {
   DBIR_REQUIRE(partials1 && stats && slots1 > 0 && (c1 + c2) % 32 == 0, "dbir_gn_finalize: bad args");
   DBIR_REQUIRE(c2 == 0 || (partials2 && slots2 > 0), "dbir_gn_finalize: second source missing");
-  gn_finalize_kernel<<<dim3(32, n), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      partials1, slots1, c1, partials2, slots2, c2, hw, eps, stats);
-  DBIR_CHECK_CUDA(cudaGetLastError());
+  DBIR_CHECK_CUDA(dbir_launch(gn_finalize_kernel, dim3(32, n), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream),
+                              partials1, slots1, c1, partials2, slots2, c2, hw, eps, stats));
   return 0;
 }
 
@@ -364,10 +371,9 @@ extern "C" int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, i
   if (ppc < 1) ppc = 1;
   ctas = (hw + ppc - 1) / ppc;
   const size_t smem = do_norm ? static_cast<size_t>(C) * 2 * sizeof(float) : 0;
-  gn_apply_kernel<<<dim3(ctas, n), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src1, src2, c1, c2, h, w, stats, gamma, beta, do_norm, do_silu, upsample,
-      reinterpret_cast<op_t*>(out), reinterpret_cast<op_t*>(out_raw), ppc);
-  DBIR_CHECK_CUDA(cudaGetLastError());
+  DBIR_CHECK_CUDA(dbir_launch(gn_apply_kernel, dim3(ctas, n), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream),
+                              src1, src2, c1, c2, h, w, stats, gamma, beta, do_norm, do_silu, upsample,
+                              reinterpret_cast<op_t*>(out), reinterpret_cast<op_t*>(out_raw), ppc));
   return 0;
 }
 
@@ -379,12 +385,12 @@ extern "C" int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t
                "dbir_layernorm: unsupported width %d (ldo %lld)", c, (long long)ldo);
   const int rows_per_cta = 8;
   const int grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  const long long ldx_ = ldx, ldo_ = ldo;
   if (out_kind == 0)
-    layernorm_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, ldx, rows, c, gamma, beta, eps, out, ldo);
+    DBIR_CHECK_CUDA(dbir_launch(layernorm_kernel<true>, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                                x, ldx_, rows, c, gamma, beta, eps, out, ldo_));
   else
-    layernorm_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, ldx, rows, c, gamma, beta, eps, out, ldo);
-  DBIR_CHECK_CUDA(cudaGetLastError());
+    DBIR_CHECK_CUDA(dbir_launch(layernorm_kernel<false>, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                                x, ldx_, rows, c, gamma, beta, eps, out, ldo_));
   return 0;
 }

@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
 
@@ -20,6 +21,10 @@ extern "C" const char* dbir_version(void) {
   return "diffbir_b200 0.1 (sm_100a; tcgen05/TMEM/TMA)";
 }
 extern "C" int dbir_operand_kind(void) { return DBIR_OPERAND_KIND; }
+extern "C" int dbir_pdl_enabled(void) {
+  static const int on = [] { const char* e = getenv("DBIR_PDL"); return e ? atoi(e) : 1; }();
+  return on;
+}
 
 extern "C" int dbir_sm_count(void) {
   static int sms = 0;
