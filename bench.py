@@ -161,8 +161,10 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------
 def kernel_census(pipe, torch, lib):
-    """One eager ControlNet+UNet forward (batch 2 = cond/uncond of a 512^2 image) with CUDA events
-    around every tensor-core launch; returns the per-family totals and the per-shape table."""
+    """Records the tensor-core launches of one ControlNet+UNet forward (batch 2 = cond/uncond of a
+    512^2 image), then replays each kernel family back-to-back inside a CUDA graph and times the
+    replay with CUDA events on the launching stream (steady state, same buffers as the real forward).
+    Returns per-family totals and the per-shape table (per-shape numbers from per-launch events)."""
     eng = pipe.cldm.engine
     dev = eng.dev
     x = torch.randn(2, 4, 64, 64, device=dev)
@@ -170,19 +172,43 @@ def kernel_census(pipe, torch, lib):
     eng.set_context(torch.randn(2, 77, 1024, device=dev))
     eng.set_timesteps([500], 2)
     eng.load_step(0)
+    two = eng.two_streams
+    eng.two_streams = False                  # record on one stream
     eng.forward(x, ci, [1.0] * 13)
     torch.cuda.synchronize()
+    lib.record_begin()
     lib.profile_begin()
     eng.forward(x, ci, [1.0] * 13)
     recs = lib.profile_end()
-    fam = {}
-    shapes = {}
+    calls = lib.record_end()
+    eng.two_streams = two
+    fam, shapes = {}, {}
+    names = {"gemm": "gemm+conv (gemm_tc_kernel)", "conv": "gemm+conv (gemm_tc_kernel)",
+             "attention": "attention (attn_fwd_kernel)"}
     for kind, info, flops, ms in recs:
-        k = "gemm+conv (gemm_tc_kernel)" if kind in ("gemm", "conv") else "attention (attn_fwd_kernel)"
-        f = fam.setdefault(k, [0.0, 0.0, 0])
-        f[0] += flops; f[1] += ms; f[2] += 1
         s = shapes.setdefault((kind,) + tuple(info), [0.0, 0.0, 0])
         s[0] += flops; s[1] += ms; s[2] += 1
+    for fname in set(names.values()):
+        sel = [c for c in calls if names[c[0]] == fname]
+        if not sel:
+            continue
+        for c in sel:
+            c[3]()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for c in sel:
+                c[3]()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        fam[fname] = [sum(c[2] for c in sel), e0.elapsed_time(e1) / reps, len(sel)]
     return fam, shapes
 
 

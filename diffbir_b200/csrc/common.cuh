@@ -87,7 +87,9 @@ extern "C" int dbir_sm_count(void);
 // set up (lets the NEXT kernel's CTAs be scheduled and run their prologue: barrier init, TMEM
 // alloc, descriptor prefetch) and pdl_wait() before touching memory written by its predecessors
 // (griddepcontrol.wait returns when all prerequisite grids completed and flushed). Hides the
-// ~2.5 us kernel-to-kernel latency of the ~600 dependent kernels per forward. DBIR_PDL=0 disables.
+// kernel-to-kernel latency of the ~600 dependent kernels per forward. Measured on B200 inside the
+// captured graph: 7.59 ms vs 7.65 ms per forward, i.e. the graph already hides most of it, so PDL is
+// opt-in (DBIR_PDL=1).
 // ---------------------------------------------------------------------------
 extern "C" int dbir_pdl_enabled(void);
 template <typename... KArgs, typename... Args>

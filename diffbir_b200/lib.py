@@ -80,6 +80,22 @@ def profile_end():
     return out
 
 
+_record = None    # list of (kind, info, flops, thunk) while recording
+
+
+def record_begin():
+    """Records every GEMM / attention launch (arguments included) so bench.py can replay exactly the
+    tensor-core kernels of one forward inside a CUDA graph and time them with CUDA events."""
+    global _record
+    _record = []
+
+
+def record_end():
+    global _record
+    out, _record = _record, None
+    return out
+
+
 class _Prof:
     def __init__(self, kind, info, flops):
         self.kind, self.info, self.flops = kind, info, flops
@@ -159,6 +175,10 @@ def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual
     g.gn_rows_per_img = gn_rows_per_img
     with _Prof("conv" if conv is not None else "gemm", (M, N, K), 2.0 * M * N * K):
         check(lib.dbir_gemm(C.byref(g), C.c_void_p(stream_ptr())), "dbir_gemm")
+    if _record is not None:
+        keep = (a, b, out, bias, rowvec, residual, splitk_ws, gn_partials)     # keep buffers alive
+        _record.append(("conv" if conv is not None else "gemm", (M, N, K), 2.0 * M * N * K,
+                        lambda g=g, keep=keep: check(lib.dbir_gemm(C.byref(g), C.c_void_p(stream_ptr())), "dbir_gemm")))
     count_launch()
 
 
@@ -172,10 +192,14 @@ def _fp(t):
 
 def attention(q, k, v, out, *, batch, heads, sq, skv, ldq, ldk, ldv, ldo):
     """Flash attention, head_dim 64; q/k/v/out are op16 tensors (possibly column slices)."""
-    with _Prof("attention", (batch, heads, sq, skv), 4.0 * batch * heads * sq * skv * 64):
+    def call():
         check(load().dbir_attention(_fp(q), _fp(k), _fp(v), _fp(out), batch, heads, sq, skv,
                                     C.c_int64(ldq), C.c_int64(ldk), C.c_int64(ldv), C.c_int64(ldo),
                                     _sp()), "dbir_attention")
+    with _Prof("attention", (batch, heads, sq, skv), 4.0 * batch * heads * sq * skv * 64):
+        call()
+    if _record is not None:
+        _record.append(("attention", (batch, heads, sq, skv), 4.0 * batch * heads * sq * skv * 64, call))
     count_launch()
 
 
