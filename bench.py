@@ -301,8 +301,16 @@ def run_ours(args):
     gf, gms, gn = fam[gname]
     achieved = gf / (gms * 1e-3) / 1e12
     forward_ms = sum(v[1] for v in fam.values())
+    traffic = None
+    tpath = ROOT / "profiles" / "r01_ncu_full_summary.json"
+    if tpath.exists():       # dram bytes (read + write) per launch from the committed `ncu --set full` capture
+        rows = [r for r in json.loads(tpath.read_text()) if "gemm_tc_kernel" in r["kernel"]]
+        if rows:
+            traffic = {"dram_bytes_per_launch_mean": sum(r["dram_bytes"] for r in rows) / len(rows),
+                       "l2_to_sm_bytes_per_launch_mean": sum(r["l2_to_sm_bytes"] for r in rows) / len(rows),
+                       "launches": len(rows), "source": "profiles/r01_ncu_full_summary.json"}
     roof = {"bound": "tensor", "kernel": gname, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
             "launches_per_forward": gn, "algorithmic_gflop_per_forward": gf / 1e9,
             "kernel_ms_per_forward": gms,
             "attention": {"achieved": fam.get("attention (attn_fwd_kernel)", [0, 1, 0])[0] /
