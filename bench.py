@@ -177,21 +177,14 @@ def kernel_census(pipe, torch, lib):
     eng.forward(x, ci, [1.0] * 13)
     torch.cuda.synchronize()
     lib.record_begin()
-    lib.profile_begin()
     eng.forward(x, ci, [1.0] * 13)
-    recs = lib.profile_end()
     calls = lib.record_end()
     eng.two_streams = two
     fam, shapes = {}, {}
     names = {"gemm": "gemm+conv (gemm_tc_kernel)", "conv": "gemm+conv (gemm_tc_kernel)",
              "attention": "attention (attn_fwd_kernel)"}
-    for kind, info, flops, ms in recs:
-        s = shapes.setdefault((kind,) + tuple(info), [0.0, 0.0, 0])
-        s[0] += flops; s[1] += ms; s[2] += 1
-    for fname in set(names.values()):
-        sel = [c for c in calls if names[c[0]] == fname]
-        if not sel:
-            continue
+
+    def replay_ms(sel, reps=5):
         for c in sel:
             c[3]()
         torch.cuda.synchronize()
@@ -202,13 +195,22 @@ def kernel_census(pipe, torch, lib):
         g.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
         e0.record()
         for _ in range(reps):
             g.replay()
         e1.record()
         torch.cuda.synchronize()
-        fam[fname] = [sum(c[2] for c in sel), e0.elapsed_time(e1) / reps, len(sel)]
+        return e0.elapsed_time(e1) / reps
+
+    for fname in set(names.values()):
+        sel = [c for c in calls if names[c[0]] == fname]
+        if sel:
+            fam[fname] = [sum(c[2] for c in sel), replay_ms(sel), len(sel)]
+    by_shape = {}
+    for c in calls:
+        by_shape.setdefault((c[0],) + tuple(c[1]), []).append(c)
+    for k, sel in by_shape.items():      # per-shape: the launches of that shape back-to-back in a graph
+        shapes[k] = [sum(c[2] for c in sel), replay_ms(sel, 3), len(sel)]
     return fam, shapes
 
 
