@@ -239,14 +239,18 @@ __device__ __forceinline__ void finish_chunk(const GemmParams& p, EpiCtx& e, flo
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, BN <= 160 ? 2 : 1)
+// EW = number of epilogue warps: 4 (two CTAs per SM, epilogue of one overlaps the mainloop of the
+// other) or 8 (grids that leave <= 1 CTA per SM: two warps per TMEM lane quarter take alternate
+// 32-column chunks, halving the exposed epilogue latency).
+template <int BN, int STAGES, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, (BN <= 160 && EW == 4) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
                const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static_assert(STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) >= 16 * EPI_TILE_BYTES, "epilogue staging must fit in the pipeline stages");
+  static_assert(STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) >= EW * 4 * EPI_TILE_BYTES, "epilogue staging must fit in the pipeline stages");
+  constexpr int CSTEP = 32 * (EW / 4);        // column stride between the chunks of one warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -255,8 +259,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
-  uint64_t* res_bars = tmem_full + 1;                 // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + 8);
+  uint64_t* res_bars = tmem_full + 1;                 // [EW warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + 2 * EW);
   uint32_t* split_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
@@ -287,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&res_bars[i], 1);
+    for (int i = 0; i < 2 * EW; ++i) mbar_init(&res_bars[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -338,14 +342,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       umma_commit(tmem_full);     // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 -------------
+    // ---------------- epilogue: warps 2.., TMEM lane quarter = warp % 4 -------------
     const int q = warp & 3;
+    const int ew = warp - 2;                // epilogue warp index
+    const int c_first = (ew >> 2) * 32;     // first chunk of this warp (EW == 8: warps 6..9 start at column 32)
     const int r = q * 32 + lane;            // accumulator row within the tile
     long long out_row = -1;                 // global output row (bias_per_row / rowvec index), -1 = masked
     int vec_idx = 0;
     EpiCtx e;
     e.tm_out = &tma_out; e.tm_res = &tma_res;
-    e.res_bar = smem_u32(res_bars + q * 2);
+    e.res_bar = smem_u32(res_bars + ew * 2);
     e.row0 = m_tile * BM + q * 32;
     e.x = e.y = e.n = 0;
     if (p.mode == 0) {
@@ -380,7 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (p.dbg) t_acc = clock64();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     // all MMAs have retired -> the pipeline stages are free: 4 staging tiles (4 KB) per warp
-    e.epi_base = smem_u32(sA) + q * (4 * EPI_TILE_BYTES);
+    e.epi_base = smem_u32(sA) + ew * (4 * EPI_TILE_BYTES);
 
     constexpr int OUT_COLS = BN;            // accumulator columns that produce output (GEGLU: BN/2)
     const bool finalize = p.splits == 1;
@@ -389,12 +395,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // prefetch the first two residual tiles
       if (finalize && p.has_residual) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-          if (c * 32 < OUT_COLS && col_base + c * 32 < p.N) epi_issue_residual(p, e, lane, c, col_base + c * 32);
+        for (int c = 0; c < 2; ++c) {
+          const int cc = c_first + c * CSTEP;
+          if (cc < OUT_COLS && col_base + cc < p.N) epi_issue_residual(p, e, lane, c, col_base + cc);
+        }
       }
       int ci = 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_first; c0 < BN; c0 += CSTEP) {
         uint32_t acc[32];
         __syncwarp();
         tmem_ld32(taddr + c0, acc);
@@ -409,37 +417,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (gc0 >= p.N) continue;
         const int ncols = min(32, p.N - gc0);
-        const int ngc = gc0 + 64;
+        const int ngc = gc0 + 2 * CSTEP;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-        finish_chunk(p, e, v, lane, ci, gc0, ncols, (c0 + 64 < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true);
+        finish_chunk(p, e, v, lane, ci, gc0, ncols, (c0 + 2 * CSTEP < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true);
         ++ci;
       }
       if (p.splits > 1) {
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
         if (threadIdx.x == 64) {
           const unsigned int t = atomicAdd(&p.tickets[tile_lin], 1u);
           const bool last = (t == static_cast<unsigned int>(p.splits) - 1);
           if (last) p.tickets[tile_lin] = 0;        // self-reset for the next launch
           *split_flag = last ? 1u : 0u;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
         if (*split_flag) {
           __threadfence();
           if (p.has_residual) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-              if (c * 32 < BN && col_base + c * 32 < p.N) epi_issue_residual(p, e, lane, c, col_base + c * 32);
+            for (int c = 0; c < 2; ++c) {
+              const int cc = c_first + c * CSTEP;
+              if (cc < BN && col_base + cc < p.N) epi_issue_residual(p, e, lane, c, col_base + cc);
+            }
           }
           int cj = 0;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = c_first; c0 < BN; c0 += CSTEP) {
             const int gc0 = col_base + c0;
             if (gc0 >= p.N) continue;
             const int ncols = min(32, p.N - gc0);
-            const int ngc = gc0 + 64;
+            const int ngc = gc0 + 2 * CSTEP;
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -448,7 +458,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += __ldcg(wcol + j * BM);
             }
-            finish_chunk(p, e, v, lane, cj, gc0, ncols, (c0 + 64 < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true);
+            finish_chunk(p, e, v, lane, cj, gc0, ncols, (c0 + 2 * CSTEP < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true);
             ++cj;
           }
         }
@@ -461,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if constexpr (HB % 32 == 0) {
         int ci = 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < HB; c0 += 32) {
+        for (int c0 = c_first; c0 < HB; c0 += CSTEP) {
           uint32_t av[32], ag[32];
           __syncwarp();
           tmem_ld32(taddr + c0, av);
@@ -501,17 +511,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
            const GemmParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 512;
   static bool configured = false;
   if (!configured) {
-    DBIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
+    DBIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  DBIR_CHECK_CUDA(dbir_launch(gemm_tc_kernel<BN, STAGES>, grid, dim3(192), smem, st, ta, tb, to, tr, p));
+  DBIR_CHECK_CUDA(dbir_launch(gemm_tc_kernel<BN, STAGES, EW>, grid, dim3(64 + 32 * EW), smem, st, ta, tb, to, tr, p));
   return 0;
 }
 
@@ -687,12 +697,16 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
     if (dbir_make_tmap(&tb, a->b, 2, dims, strides, box, 2, 1)) return -3;
   }
   dim3 grid(m_tiles, (a->N + bn - 1) / bn, plan.splits);
+  // <= one CTA per SM anyway -> 8 epilogue warps and a deeper pipeline; else two CTAs per SM
+  static const int wide_mode = [] { const char* e = getenv("DBIR_GEMM_WIDE"); return e ? atoi(e) : -1; }();
+  const bool wide = wide_mode >= 0 ? wide_mode != 0
+                                   : static_cast<long long>(grid.x) * grid.y * grid.z <= dbir_sm_count();
   switch (bn) {
-    case 32:  return launch<32, 5>(ta, tb, to, tr, p, grid, st);
-    case 64:  return launch<64, 4>(ta, tb, to, tr, p, grid, st);
-    case 128: return launch<128, 3>(ta, tb, to, tr, p, grid, st);
-    case 160: return launch<160, 3>(ta, tb, to, tr, p, grid, st);
-    case 256: return launch<256, 4>(ta, tb, to, tr, p, grid, st);
+    case 32:  return wide ? launch<32, 7, 8>(ta, tb, to, tr, p, grid, st) : launch<32, 5, 4>(ta, tb, to, tr, p, grid, st);
+    case 64:  return wide ? launch<64, 6, 8>(ta, tb, to, tr, p, grid, st) : launch<64, 4, 4>(ta, tb, to, tr, p, grid, st);
+    case 128: return wide ? launch<128, 4, 8>(ta, tb, to, tr, p, grid, st) : launch<128, 3, 4>(ta, tb, to, tr, p, grid, st);
+    case 160: return wide ? launch<160, 4, 8>(ta, tb, to, tr, p, grid, st) : launch<160, 3, 4>(ta, tb, to, tr, p, grid, st);
+    case 256: return wide ? launch<256, 4, 8>(ta, tb, to, tr, p, grid, st) : launch<256, 4, 4>(ta, tb, to, tr, p, grid, st);
     default:
       dbir_set_error("dbir_gemm: unsupported tile width %d", bn);
       return -2;
