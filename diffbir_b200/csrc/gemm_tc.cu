@@ -60,6 +60,10 @@ struct GemmParams {
   // squares over the warp's rows -> stats[(img * nslots + slot) * N + col][2] (fp32 outputs only)
   float* stats;
   int stats_nslots, stats_rows_per_img, stats_slots_x;
+  // L2 prefetch of memory a LATER kernel will stream (the next layers' weights): issued by the
+  // epilogue warps while they wait for the mainloop
+  const char* pf_ptr;
+  long long pf_bytes;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float prm) {
@@ -381,6 +385,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         e.stats_base = (static_cast<long long>(e.n) * p.stats_nslots + slot) * p.N;
       }
     }
+    if (p.pf_bytes > 0) {
+      // one 128-byte line per prefetch; lines are spread over every epilogue thread of the grid
+      const long long nthr = static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * (32 * EW);
+      const long long me = ((static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (32 * EW) +
+                           (threadIdx.x - 64);
+      for (long long off = me * 128; off < p.pf_bytes; off += nthr * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf_ptr + off));
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     if (p.dbg) t_acc = clock64();
@@ -593,6 +605,8 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
   p.alpha = a->alpha; p.act = a->act; p.act_param = a->act_param; p.geglu = a->geglu;
   p.bias_per_row = a->bias_per_row;
   p.dbg = reinterpret_cast<long long*>(a->debug_stamps);
+  p.pf_ptr = reinterpret_cast<const char*>(a->prefetch_ptr);
+  p.pf_bytes = a->prefetch_ptr ? a->prefetch_bytes : 0;
   if (a->geglu)
     DBIR_REQUIRE(a->force_bn >= 64 && a->force_bn != 160 && a->N % a->force_bn == 0 && !a->residual,
                  "dbir_gemm: GEGLU needs force_bn in {64,128,256} dividing N (weights are packed per tile)");

@@ -145,6 +145,8 @@ class CldmEngine:
         self._side = None
         self._ts_key = None
         self._part = {}                  # fp32 activation data_ptr -> (GN partial-sum buffer, slots)
+        self._wseq, self._wpos = {}, {}  # per-stream weight sequence of the forward (L2 prefetch lookahead)
+        self.prefetch_weights = True
         self.fuse_gn_stats = True
         self.emb_cur = None
         self._graphs = {}                # (shape, scales) -> (CUDAGraph, x_in, c_img, eps, launches)
@@ -214,10 +216,25 @@ class CldmEngine:
         """Selects the time embedding of sampler step `step_idx` (one D2D copy, outside graphs)."""
         self.emb_cur.copy_(self.emb_table[step_idx])
 
-    def _gemm(self, tag: str, *args, **kw):
-        """dbir_gemm with this stream's split-K scratch (64 MiB, zero-initialised once)."""
+    def _gemm(self, tag: str, a, b, *args, **kw):
+        """dbir_gemm with this stream's split-K scratch (64 MiB, zero-initialised once) and an L2
+        prefetch of the weights of the GEMM that follows on the same stream (weights are the only
+        cold operand of a forward: 2.5 GB streamed from HBM per step, activations are L2-resident).
+        The weight sequence is learnt on the previous forward (it never changes)."""
         ws = self.ws.get(tag + ":splitk", (16 * 1024 * 1024 + 16384,), torch.float32, zero=True)
-        lib.gemm(*args, splitk_ws=ws, **kw)
+        seq = self._wseq.setdefault(tag, [])
+        i = self._wpos.get(tag, 0)
+        wbytes = b.numel() * b.element_size()
+        if i < len(seq):
+            if seq[i][0] != b.data_ptr():          # sequence changed (other shapes): relearn
+                del seq[i:]
+        if i >= len(seq):
+            seq.append((b.data_ptr(), wbytes))
+        self._wpos[tag] = i + 1
+        pf = None
+        if self.prefetch_weights and i + 1 < len(seq):
+            pf = seq[i + 1]
+        lib.gemm(a, b, *args, splitk_ws=ws, prefetch=pf, **kw)
 
     def _emb(self, tag: str, l: arch.Layer, nb: int) -> torch.Tensor:
         o = self.emb_offsets[tag + l.prefix]
@@ -392,6 +409,7 @@ class CldmEngine:
         assert c_img.is_cuda and c_img.dtype == torch.float32 and c_img.is_contiguous()
         nb, _, h, w = x.shape
         assert nb == self._nb == self.emb_nb, "set_context / set_timesteps batch mismatch"
+        self._wpos = {}
         ws, U, Cn = self.ws, self.unet, self.cnet
         # 1+2. UNet encoder + middle on the current stream, ControlNet concurrently on a side
         #      stream (their small 16x16 / 8x8 layers each fill only part of the 148 SMs);

@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("split_k", C.c_int32), ("reserved1", C.c_int32),
         ("debug_stamps", C.c_void_p),
         ("gn_partials", C.c_void_p), ("gn_rows_per_img", C.c_int32), ("reserved2", C.c_int32),
+        ("prefetch_ptr", C.c_void_p), ("prefetch_bytes", C.c_int64),
     ]
 
 
@@ -140,7 +141,7 @@ ACT = {None: 0, "none": 0, "gelu": 1, "lrelu": 2, "silu": 3}
 def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual=None,
          lda=0, ldb=0, ldo=None, ldr=None, conv=None, act=None, act_param=0.0, alpha=1.0,
          geglu=False, force_bn=0, bias_per_row=False, out2=None, ldo2=None, splitk_ws=None,
-         split_k=0, debug_stamps=None, gn_partials=None, gn_rows_per_img=0):
+         split_k=0, debug_stamps=None, gn_partials=None, gn_rows_per_img=0, prefetch=None):
     """out = residual + alpha * act(A @ B^T + bias + rowvec). conv = (n, h, w, c, ksize)."""
     lib = load()
     g = GemmArgs()
@@ -173,6 +174,8 @@ def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual
     g.debug_stamps = _ptr(debug_stamps)
     g.gn_partials = _ptr(gn_partials)
     g.gn_rows_per_img = gn_rows_per_img
+    if prefetch is not None:
+        g.prefetch_ptr, g.prefetch_bytes = prefetch
     with _Prof("conv" if conv is not None else "gemm", (M, N, K), 2.0 * M * N * K):
         check(lib.dbir_gemm(C.byref(g), C.c_void_p(stream_ptr())), "dbir_gemm")
     if _record is not None:

@@ -67,6 +67,8 @@ typedef struct dbir_gemm_args {
                            sums of squares of the OUTPUT (fused GroupNorm statistics; see dbir_gn_finalize) */
   int32_t gn_rows_per_img; /* matrix mode only: rows per image (multiple of 32); conv mode uses img_h*img_w */
   int32_t reserved2;
+  const void* prefetch_ptr; /* optional: memory a later kernel will stream (next layers' weights); pulled into */
+  int64_t prefetch_bytes;   /* L2 by the idle epilogue warps during this kernel's mainloop */
 } dbir_gemm_args;
 /* Number of 32-row slots per image dbir_gemm writes into gn_partials (conv: h, w > 0; matrix: rows_per_img). */
 int32_t dbir_gemm_gn_slots(int32_t conv_h, int32_t conv_w, int32_t rows_per_img);
