@@ -149,17 +149,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 #pragma unroll
       for (int c0 = 0; c0 < TK; c0 += 32) tmem_ld32(t_s + c0, s + c0);
       tmem_ld_wait();
-      float m_tile = -INFINITY;
+      // 8 independent max chains (a single chain would expose 127 dependent FMNMX latencies)
+      float mx[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) mx[a] = -INFINITY;
       if (valid == TK) {
 #pragma unroll
-        for (int i = 0; i < TK; ++i) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
+        for (int i = 0; i < TK; ++i) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[i]));
       } else {
 #pragma unroll
         for (int i = 0; i < TK; ++i)
-          if (i < valid) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
+          if (i < valid) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[i]));
       }
+      const float m_tile = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                                 fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
       const float m_new = fmaxf(m_run, m_tile);
-      const float alpha = exp2f((m_run - m_new) * sl2);
+      float alpha;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"((m_run - m_new) * sl2));
       const float mb = m_new * sl2;
       // PV(j-1) must have retired before P is overwritten and before O is rescaled
       if (j > 0) {
@@ -180,21 +186,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
           tmem_st_wait();
         }
       }
-      float l_tile = 0.f;
+      float ls[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) ls[a] = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < TK; c0 += 8) {
         float e[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float x = exp2f(__uint_as_float(s[c0 + i]) * sl2 - mb);
+          // arguments are <= 0: one MUFU.EX2 (ex2.approx.ftz), no range fix-ups needed
+          float x;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(fmaf(__uint_as_float(s[c0 + i]), sl2, -mb)));
           e[i] = (valid == TK || c0 + i < valid) ? x : 0.f;
-          l_tile += e[i];
+          ls[i] += e[i];
         }
         uint4 t;
         t.x = pack2(e[0], e[1]); t.y = pack2(e[2], e[3]); t.z = pack2(e[4], e[5]); t.w = pack2(e[6], e[7]);
         // 16-byte chunk (c0 % 64) / 8 of sub-tile c0 / 64, 128-byte swizzle
         *reinterpret_cast<uint4*>(p_row + (c0 >> 6) * TILE_BYTES + (((((c0 & 63) >> 3)) ^ sw) << 4)) = t;
       }
+      const float l_tile = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
       tc_fence_before();
