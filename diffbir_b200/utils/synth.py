@@ -66,8 +66,10 @@ def synthetic_sd_checkpoint(unet_cfg=None, vae_cfg=None, clip_cfg=None, seed: in
     return sd
 
 
-def build_synthetic_pipeline(device="cuda", seed: int = 1234, small: bool = False):
-    """SwinIRPipeline on synthetic weights. small=True uses the reduced test architectures."""
+def build_synthetic_pipeline(device="cuda", seed: int = 1234, small: bool = False, v_prediction: bool = False):
+    """SwinIRPipeline on synthetic weights. small=True uses the reduced test architectures;
+    v_prediction=True uses the v2.1 diffusion settings (v-parameterization, zero terminal SNR:
+    reference configs/inference/diffusion_v2.1.yaml)."""
     from .. import arch
     from ..model import ControlLDM, Diffusion, SwinIR
     from ..pipeline import SwinIRPipeline
@@ -96,7 +98,8 @@ def build_synthetic_pipeline(device="cuda", seed: int = 1234, small: bool = Fals
                   mlp_ratio=scfg["mlp_ratio"], sf=8, img_range=1.0, upsampler="nearest+conv",
                   resi_connection="1conv", unshuffle=True, unshuffle_scale=8, device=device)
     swin.load_state_dict(make_state_dict(arch.swinir_shapes(scfg), seed + 4))
-    diffusion = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000)
+    diffusion = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000,
+                          parameterization="v" if v_prediction else "eps", zero_snr=v_prediction)
     return SwinIRPipeline(swin, cldm, diffusion, None, device)
 
 

@@ -42,6 +42,7 @@ def _oracle_run(pipe, lq, small, seed=231, **kw):
             betas=pipe.diffusion.betas, parameterization=pipe.diffusion.parameterization,
             steps=kw["steps"], strength=kw["strength"], pos_prompt=kw["pos_prompt"], neg_prompt=kw["neg_prompt"],
             cfg_scale=kw["cfg_scale"], sampler=kw["sampler_type"], cldm_tiled=kw["cldm_tiled"],
+            rescale_cfg=kw["rescale_cfg"],
             cldm_tile_size=kw["cldm_tile_size"], cldm_tile_stride=kw["cldm_tile_stride"], device=dev,
             set_strength=lambda s: scales.update(s=[s] * 13), taps=taps)
     return out, taps
@@ -52,9 +53,9 @@ def _psnr_u8(a, b):
     return float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
 
 
-def _pipe(small):
+def _pipe(small, v_prediction=False):
     no_tf32()
-    pipe = build_synthetic_pipeline("cuda", seed=1234, small=small)
+    pipe = build_synthetic_pipeline("cuda", seed=1234, small=small, v_prediction=v_prediction)
     scfg = dict(arch.SWINIR_CFG, depths=(2, 2), num_heads=(6, 6)) if small else arch.SWINIR_CFG
     pipe.cleaner.engine_sd = make_state_dict(arch.swinir_shapes(scfg), 1234 + 4)
     pipe.taps = {}
@@ -76,6 +77,22 @@ def test_small_pipeline_matches_oracle(sampler, steps, tiled):
     print(f"small {sampler} x{steps} tiled={tiled}: latent rel-rms {e:.2e}, uint8 PSNR {p:.1f} dB, "
           f"differing pixels {(out != ref).mean() * 100:.1f}%")
     assert out.shape == ref.shape == lq.shape and out.dtype == np.uint8
+    assert e < 2e-2 and p > 45.0
+
+
+@pytest.mark.parametrize("sampler,rescale", [("spaced", False), ("ddim", True)])
+def test_small_pipeline_v_prediction(sampler, rescale):
+    """v2.1 settings (BASELINE configs[4]): v-parameterization, zero terminal SNR, optional cfg rescale."""
+    pipe = _pipe(True, v_prediction=True)
+    lq = synthetic_lq(512, 512, seed=2)
+    kw = dict(RUN_DEFAULTS, steps=10, sampler_type=sampler, rescale_cfg=rescale)
+    torch.manual_seed(231)
+    out = pipe.run(lq, **kw)
+    ref, taps = _oracle_run(pipe, lq, True, **kw)
+    zp, zr = pipe.taps["z"], taps["z"]
+    e = ((zp - zr).pow(2).mean().sqrt() / zr.pow(2).mean().sqrt()).item()
+    p = _psnr_u8(out, ref)
+    print(f"small v-pred {sampler} rescale={rescale}: latent rel-rms {e:.2e}, uint8 PSNR {p:.1f} dB")
     assert e < 2e-2 and p > 45.0
 
 
