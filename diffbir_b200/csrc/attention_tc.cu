@@ -165,7 +165,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                                  fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
       const float m_new = fmaxf(m_run, m_tile);
       float alpha;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"((m_run - m_new) * sl2));
+      alpha = ex2_approx((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
       // PV(j-1) must have retired before P is overwritten and before O is rescaled
       if (j > 0) {
@@ -180,7 +180,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             tmem_ld16(t_o + c0, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            for (int i = 0; i < 16; i += 2) {
+              float y0, y1;
+              fmul2(y0, y1, __uint_as_float(o[i]), __uint_as_float(o[i + 1]), alpha, alpha);
+              o[i] = __float_as_uint(y0); o[i + 1] = __float_as_uint(y1);
+            }
             tmem_st16(t_o + c0, o);
           }
           tmem_st_wait();
@@ -189,21 +193,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       float ls[8];
 #pragma unroll
       for (int a = 0; a < 8; ++a) ls[a] = 0.f;
+      const float nmb = -mb;
+      if (valid == TK) {
+        // full tile: packed FFMA2 / FADD2, no masking
 #pragma unroll
-      for (int c0 = 0; c0 < TK; c0 += 8) {
-        float e[8];
+        for (int c0 = 0; c0 < TK; c0 += 8) {
+          float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // arguments are <= 0: one MUFU.EX2 (ex2.approx.ftz), no range fix-ups needed
-          float x;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(fmaf(__uint_as_float(s[c0 + i]), sl2, -mb)));
-          e[i] = (valid == TK || c0 + i < valid) ? x : 0.f;
-          ls[i] += e[i];
+          for (int i = 0; i < 8; i += 2) {
+            float x0, x1;
+            ffma2(x0, x1, __uint_as_float(s[c0 + i]), __uint_as_float(s[c0 + i + 1]), sl2, sl2, nmb, nmb);
+            // arguments are <= 0: one MUFU.EX2 (ex2.approx.ftz), no range fix-ups needed
+            e[i] = ex2_approx(x0);
+            e[i + 1] = ex2_approx(x1);
+            fadd2(ls[i], ls[i + 1], ls[i], ls[i + 1], e[i], e[i + 1]);
+          }
+          uint4 t;
+          t.x = pack2(e[0], e[1]); t.y = pack2(e[2], e[3]); t.z = pack2(e[4], e[5]); t.w = pack2(e[6], e[7]);
+          // 16-byte chunk (c0 % 64) / 8 of sub-tile c0 / 64, 128-byte swizzle
+          *reinterpret_cast<uint4*>(p_row + (c0 >> 6) * TILE_BYTES + (((((c0 & 63) >> 3)) ^ sw) << 4)) = t;
         }
-        uint4 t;
-        t.x = pack2(e[0], e[1]); t.y = pack2(e[2], e[3]); t.z = pack2(e[4], e[5]); t.w = pack2(e[6], e[7]);
-        // 16-byte chunk (c0 % 64) / 8 of sub-tile c0 / 64, 128-byte swizzle
-        *reinterpret_cast<uint4*>(p_row + (c0 >> 6) * TILE_BYTES + (((((c0 & 63) >> 3)) ^ sw) << 4)) = t;
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < TK; c0 += 8) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = ex2_approx(fmaf(__uint_as_float(s[c0 + i]), sl2, nmb));
+            e[i] = c0 + i < valid ? x : 0.f;
+            ls[i] += e[i];
+          }
+          uint4 t;
+          t.x = pack2(e[0], e[1]); t.y = pack2(e[2], e[3]); t.z = pack2(e[4], e[5]); t.w = pack2(e[6], e[7]);
+          *reinterpret_cast<uint4*>(p_row + (c0 >> 6) * TILE_BYTES + (((((c0 & 63) >> 3)) ^ sw) << 4)) = t;
+        }
       }
       const float l_tile = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
       l_run = l_run * alpha + l_tile;
