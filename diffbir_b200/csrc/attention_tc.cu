@@ -85,49 +85,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   pdl_trigger();
   pdl_wait();
 
+  // Warps 0 / 1 run warp-uniform loops and elect one lane per TMA / MMA / commit: inside a plain
+  // `if (lane == 0)` region the compiler serialises every such instruction through a per-lane loop.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&bar->q_full, TILE_BYTES);
       tma_load_3d(sQ, &tma_q, &bar->q_full, head * DH, q0, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&bar->kv_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % KV_STAGES;
+      const uint32_t ph = (j / KV_STAGES) & 1;
+      mbar_wait(&bar->kv_empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bar->kv_full[s], 2 * TILE_BYTES);
         tma_load_3d(sK + s * TILE_BYTES, &tma_k, &bar->kv_full[s], head * DH, j * TK, b);
         tma_load_3d(sV + s * TILE_BYTES, &tma_v, &bar->kv_full[s], head * DH, j * TK, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc(TK, 0, 0);   // S[128 x 128]: Q, K both K-major
-      constexpr uint32_t idesc_o = umma_idesc(DH, 0, 1);   // O[128 x 64]: P K-major, V MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
-      mbar_wait(&bar->q_full, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        const uint32_t k_addr = smem_u32(sK + s * TILE_BYTES);
-        const uint32_t v_addr = smem_u32(sV + s * TILE_BYTES);
-        mbar_wait(&bar->kv_full[s], ph);
-        tc_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc(TK, 0, 0);   // S[128 x 128]: Q, K both K-major
+    constexpr uint32_t idesc_o = umma_idesc(DH, 0, 1);   // O[128 x 64]: P K-major, V MN-major
+    const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
+    const uint64_t p_desc = umma_desc_sw128(smem_u32(sP));
+    const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK));
+    const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV));
+    mbar_wait(&bar->q_full, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % KV_STAGES;
+      const uint32_t ph = (j / KV_STAGES) & 1;
+      // descriptor start addresses advance in 16-byte units
+      const uint64_t k_desc = k_desc0 + static_cast<uint64_t>((s * TILE_BYTES) >> 4);
+      const uint64_t v_desc = v_desc0 + static_cast<uint64_t>((s * TILE_BYTES) >> 4);
+      mbar_wait(&bar->kv_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          umma_f16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32),
-                   idesc_s, k != 0 ? 1u : 0u);
+          umma_f16(tmem_base + TM_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&bar->s_full);
-        // P(j) in smem (written by the softmax warps) x V(j)
-        mbar_wait(&bar->p_full, j & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      // P(j) in smem (written by the softmax warps) x V(j)
+      mbar_wait(&bar->p_full, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < TK / 16; ++k)
-          umma_f16(tmem_base + TM_O,
-                   umma_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                   umma_desc_sw128(v_addr + k * 16 * 128), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          umma_f16(tmem_base + TM_O, p_desc + static_cast<uint64_t>(((k >> 2) * TILE_BYTES + (k & 3) * 32) >> 4),
+                   v_desc + static_cast<uint64_t>((k * 16 * 128) >> 4), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         umma_commit(&bar->o_full);
         umma_commit(&bar->kv_empty[s]);
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

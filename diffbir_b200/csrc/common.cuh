@@ -93,19 +93,35 @@ extern "C" int dbir_sm_count(void);
 // ---------------------------------------------------------------------------
 extern "C" int dbir_pdl_enabled(void);
 template <typename... KArgs, typename... Args>
-inline cudaError_t dbir_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                               cudaStream_t st, Args&&... args) {
+inline cudaError_t dbir_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t st, unsigned cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (dbir_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = dbir_pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t dbir_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                               cudaStream_t st, Args&&... args) {
+  return dbir_launch_cluster(kernel, grid, block, smem, st, 1u, static_cast<Args&&>(args)...);
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -115,6 +131,17 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// One lane of a fully converged warp (deterministic for a given mask). Single-thread work
+// (TMA, tcgen05.mma, tcgen05.commit) sits in `if (elect_one())` inside warp-uniform loops: the
+// compiler then keeps addresses / descriptors in uniform registers instead of wrapping every
+// such instruction in a per-lane serialisation loop, which a plain `if (lane == 0)` region costs.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- mbarrier --------------------------------------------------------------
@@ -278,9 +305,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
 }
 // Instruction descriptor for kind::f16, fp32 accumulate, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t n, uint32_t a_mn_major,
-                                                  uint32_t b_mn_major) {
+                                                  uint32_t b_mn_major, uint32_t m = 128u) {
   return (1u << 4) | (DBIR_UMMA_FMT << 7) | (DBIR_UMMA_FMT << 10) | (a_mn_major << 15) |
-         (b_mn_major << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+         (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                          uint32_t idesc, uint32_t accumulate) {
@@ -298,6 +325,72 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
                    "r"(smem_u32(bar))
                : "memory");
+}
+
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run one M=256 MMA;
+// each CTA holds its own 128 accumulator rows in its TMEM and stages its 128 rows of A plus HALF
+// of the B tile, so the B operand crosses the L2 fabric once per pair instead of once per CTA.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// TMA loads whose completion is signalled on a barrier of EITHER CTA of the pair (`bar_cluster` is
+// a shared::cluster address, normally the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster,
+                                                 int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "{\n.reg .b16 m;\nmov.b16 m, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n}" ::
+          "r"(smem_u32(bar))
+      : "memory");
 }
 
 // ---- misc math -------------------------------------------------------------

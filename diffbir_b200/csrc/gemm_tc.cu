@@ -21,12 +21,17 @@
 #include "common.cuh"
 #include "../../include/diffbir_b200.h"
 #include <stdlib.h>
+#include <array>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 x 16-bit = 128 B = one swizzle atom row
-constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int A_SUB_BYTES = BM * BK * 2;    // one 64-wide k-block of A
 constexpr int EPI_TILE_BYTES = 32 * 32 * 4;   // one warp's 32x32 fp32 staging tile
 
 struct GemmParams {
@@ -246,12 +251,20 @@ __device__ __forceinline__ void finish_chunk(const GemmParams& p, EpiCtx& e, flo
 // EW = number of epilogue warps: 4 (two CTAs per SM, epilogue of one overlaps the mainloop of the
 // other) or 8 (grids that leave <= 1 CTA per SM: two warps per TMEM lane quarter take alternate
 // 32-column chunks, halving the exposed epilogue latency).
-template <int BN, int STAGES, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, (BN <= 160 && EW == 4) ? 2 : 1)
+// PAIR: the two CTAs of a (2,1,1) cluster (adjacent M tiles, same N tile) run M=256 MMAs issued by
+// the even CTA (cta_group::2); each CTA stages its own A rows and half of the B tile.
+// KSUB: 64-wide k-blocks per pipeline stage. The producer / MMA-issue loops cost ~350-500 cycles per
+// iteration in barrier, TMA-issue and commit latency (measured), more than the MMAs of one k-block
+// take for BN < 256; two k-blocks per stage amortise that.
+template <int BN, int STAGES, int EW, bool PAIR, int KSUB>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
                const GemmParams p) {
-  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int B_ROWS = PAIR ? BN / 2 : BN;          // B rows staged by this CTA
+  constexpr int B_SUB_BYTES = B_ROWS * BK * 2;        // one k-block of B
+  constexpr int A_STAGE_BYTES = KSUB * A_SUB_BYTES;
+  constexpr int B_STAGE_BYTES = KSUB * B_SUB_BYTES;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static_assert(STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) >= EW * 4 * EPI_TILE_BYTES, "epilogue staging must fit in the pipeline stages");
   constexpr int CSTEP = 32 * (EW / 4);        // column stride between the chunks of one warp
@@ -269,6 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const int m_tile = blockIdx.x;
   const int n_tile = blockIdx.y;
   const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
@@ -298,52 +312,118 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int i = 0; i < 2 * EW; ++i) mbar_init(&res_bars[i], 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  // PAIR: the peer's barriers and TMEM must be live before any remote complete_tx / MMA write
+  if constexpr (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();        // the next kernel may start its prologue
   pdl_wait();           // A operand / residual come from predecessor kernels
   if (p.dbg) t_setup = clock64();
 
+  const int n_stage_iters = (kb1 - kb0 + KSUB - 1) / KSUB;
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = kb0; kb < kb1; ++kb) {
-        const int s = (kb - kb0) % STAGES;
-        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        if (p.mode == 0) {
-          tma_load_2d(sA + s * A_STAGE_BYTES, &tma_a, &full[s], kb * BK, m_tile * BM);
-        } else {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          const int dy = tap / p.kw - p.pad;
-          const int dx = tap % p.kw - p.pad;
-          tma_load_4d(sA + s * A_STAGE_BYTES, &tma_a, &full[s], cb * BK, x0 + dx, y0 + dy, n0);
+    // ---------------- TMA producer: warp-uniform loop, one elected lane issues -------------
+    const uint32_t fbar0 = PAIR ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
+    const int b_row = n_tile * BN + static_cast<int>(cta_rank) * B_ROWS;
+    // conv mode: (channel block, tap column, tap row) of the next k-block, advanced incrementally
+    // (integer divisions in this loop cost more than the TMA issue itself)
+    int cb = 0, tx = 0, ty = 0;
+    if (p.mode == 1) {
+      const int tap0 = kb0 / p.cblocks;
+      cb = kb0 - tap0 * p.cblocks;
+      ty = tap0 / p.kw;
+      tx = tap0 - ty * p.kw;
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < n_stage_iters; ++it) {
+      // coordinates of this stage's k-blocks (all lanes, so they stay in uniform registers).
+      // k-blocks past this CTA's range are fetched from out-of-range coordinates: the TMA unit
+      // zero-fills them without memory traffic and the byte count per stage stays constant.
+      int kc[KSUB], ac[KSUB], ax[KSUB], ay[KSUB];
+#pragma unroll
+      for (int j = 0; j < KSUB; ++j) {
+        const int kb = kb0 + it * KSUB + j;
+        const bool live = kb < kb1;
+        kc[j] = live ? kb * BK : p.num_kb * BK;
+        ac[j] = ax[j] = ay[j] = 0;
+        if (p.mode == 1) {
+          // conv: A is addressed by (channel block, tap offset) instead of k
+          ac[j] = live ? cb * BK : p.cblocks * BK;
+          ax[j] = x0 + tx - p.pad;
+          ay[j] = y0 + ty - p.pad;
+          if (++cb == p.cblocks) { cb = 0; if (++tx == p.kw) { tx = 0; ++ty; } }
         }
-        tma_load_2d(sB + s * B_STAGE_BYTES, &tma_b, &full[s], kb * BK, n_tile * BN);
       }
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
+        // PAIR: both CTAs' loads complete on the leader's barrier, which expects the bytes of both
+        if (cta_rank == 0) mbar_expect_tx(&full[s], (PAIR ? 2 : 1) * (A_STAGE_BYTES + B_STAGE_BYTES));
+        const uint32_t fbar = fbar0 + s * 8;
+#pragma unroll
+        for (int j = 0; j < KSUB; ++j) {
+          uint8_t* a_dst = sA + s * A_STAGE_BYTES + j * A_SUB_BYTES;
+          uint8_t* b_dst = sB + s * B_STAGE_BYTES + j * B_SUB_BYTES;
+          if (p.mode == 0) {
+            if constexpr (PAIR) tma_load_2d_pair(a_dst, &tma_a, fbar, kc[j], m_tile * BM);
+            else tma_load_2d(a_dst, &tma_a, &full[s], kc[j], m_tile * BM);
+          } else {
+            if constexpr (PAIR) tma_load_4d_pair(a_dst, &tma_a, fbar, ac[j], ax[j], ay[j], n0);
+            else tma_load_4d(a_dst, &tma_a, &full[s], ac[j], ax[j], ay[j], n0);
+          }
+          if constexpr (PAIR) tma_load_2d_pair(b_dst, &tma_b, fbar, kc[j], b_row);
+          else tma_load_2d(b_dst, &tma_b, &full[s], kc[j], b_row);
+        }
+      }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(BN, 0, 0);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        const int s = (kb - kb0) % STAGES;
-        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
+    // ---------------- MMA issuer (leader CTA of a pair only): warp-uniform loop -------------
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(BN, 0, 0, PAIR ? 256u : 128u);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_stage_iters; ++it) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
-        const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
+        if (elect_one()) {
+          // descriptors advance in units of 16 bytes (start-address field, low bits)
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((s * A_STAGE_BYTES) >> 4);
+          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((s * B_STAGE_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
-                   idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+          for (int j = 0; j < KSUB; ++j) {
+            if (kb0 + it * KSUB + j < kb1) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t da = a_desc + static_cast<uint64_t>((j * A_SUB_BYTES) >> 4) + 2 * k;
+                const uint64_t db = b_desc + static_cast<uint64_t>((j * B_SUB_BYTES) >> 4) + 2 * k;
+                const uint32_t acc = (it > 0 || j > 0 || k > 0) ? 1u : 0u;
+                if constexpr (PAIR) umma_f16_pair(tmem_base, da, db, idesc, acc);
+                else umma_f16(tmem_base, da, db, idesc, acc);
+              }
+            }
+          }
+          // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(&empty[s]);
+          else umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);   // frees the smem stage once these MMAs retire
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(tmem_full);     // accumulator complete
+      // accumulator complete
+      if (elect_one()) {
+        if constexpr (PAIR) umma_commit_pair(tmem_full);
+        else umma_commit(tmem_full);
+      }
     }
   } else {
     // ---------------- epilogue: warps 2.., TMEM lane quarter = warp % 4 -------------
@@ -516,74 +596,245 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       d[0] = t_start; d[1] = t_setup; d[2] = t_acc; d[3] = clock64();
     }
   }
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // neither CTA may retire while the other can still signal it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int BN, int STAGES, int EW>
+template <int BN, int STAGES, int EW, bool PAIR = false, int KSUB = 1>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
            const GemmParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 512;
+  constexpr int smem = STAGES * KSUB * (A_SUB_BYTES + (PAIR ? BN / 2 : BN) * BK * 2) + 1024 + 512;
+  static_assert(smem <= 227 * 1024, "pipeline does not fit in shared memory");
   static bool configured = false;
   if (!configured) {
-    DBIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EW>,
+    DBIR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EW, PAIR, KSUB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  DBIR_CHECK_CUDA(dbir_launch(gemm_tc_kernel<BN, STAGES, EW>, grid, dim3(64 + 32 * EW), smem, st, ta, tb, to, tr, p));
+  DBIR_CHECK_CUDA(dbir_launch_cluster(gemm_tc_kernel<BN, STAGES, EW, PAIR, KSUB>, grid, dim3(64 + 32 * EW), smem, st,
+                                      PAIR ? 2u : 1u, ta, tb, to, tr, p));
   return 0;
 }
 
-// Tile width + split-K factor. Cost model (cycles, per SM): the single-CTA mainloop is L2-feed
-// bound at ~3 cycles per byte-row, so a k-block costs ~3.05*(128+BN); epilogue ~20*BN; a split
-// adds a workspace round trip. CTAs are spread over `sms` SMs, a partial last wave costs a full one.
-struct TilePlan { int bn, splits, kb_per_split; };
+// Tile width, CTA pairing and split-K factor from a cost model in SM cycles, calibrated on B200
+// with the per-CTA clock64 stamps (tools/gpu_pair_timeline.py, profiles/r01_gemm_mainloop.txt):
+//   * one 64-wide k-block costs max(MMA time, loop overhead): the MMAs take ~2*BN cycles
+//     (128 x BN x 64 at 128 x 256 x 16 per 128 cycles), the producer / issue loops ~520 cycles per
+//     stage iteration (barrier, TMA-issue and commit latencies) -> ~290 per k-block with two
+//     k-blocks per stage (KSUB = 2);
+//   * two CTAs on one SM share its tensor pipe but hide each other's overhead and epilogue;
+//   * epilogue ~1500 + 28*BN cycles with 8 warps, ~500 + 55*BN with 4; split-K adds a workspace
+//     round trip; CTAs are spread over `sms` SMs, a partial last wave costs a full one.
+struct TilePlan { int bn, splits, kb_per_split, pair; };
 
-TilePlan pick_plan(int m_tiles, int N, int num_kb, int geglu, int forced_bn, int split_req,
-                   long long ws_floats_avail) {
+__host__ int plan_ksub(int bn, int pair, bool wide) {
+  if (pair) return (bn == 256 && !wide) ? 1 : 2;
+  if (bn == 256) return 1;
+  return (wide || bn <= 64) ? 2 : 1;
+}
+
+struct PlanQuery {
+  int m_tiles, N, num_kb, geglu, forced_bn, split_req, pair_req;
+  long long ws_floats_avail;
+};
+
+// Calls f(plan, modelled cost) for every plan the kernel family can run for this problem.
+template <typename F>
+void for_each_plan(const PlanQuery& q, F f) {
   const int cands[5] = {256, 160, 128, 64, 32};
   const int sms = dbir_sm_count();
-  TilePlan best{64, 1, num_kb};
-  double best_cost = -1.0;
-  for (int i = 0; i < 5; ++i) {
-    const int bn = cands[i];
-    if (forced_bn > 0 && bn != forced_bn) continue;
-    if (forced_bn <= 0) {
-      if (geglu && bn < 64) continue;
-      if (bn > 64 && N % bn != 0) continue;          // ragged N only with the narrow tiles
+  // CTA pairs (cta_group::2): DBIR_GEMM_PAIR = 0 never, 1 whenever the shape allows, unset: free choice
+  static const int pair_env = [] { const char* e = getenv("DBIR_GEMM_PAIR"); return e ? atoi(e) : -1; }();
+  const int pair_mode = q.pair_req == 1 ? 1 : q.pair_req == 2 ? 0 : pair_env;
+  const bool can_pair = pair_mode != 0 && !(q.m_tiles & 1);
+  for (int i = 0; i < 10; ++i) {
+    const int bn = cands[i % 5];
+    const int pair = 1 - i / 5;
+    if (pair && (!can_pair || bn < 64)) continue;
+    if (!pair && pair_mode == 1 && can_pair && bn >= 64) continue;     // forced pairing
+    if (q.forced_bn > 0 && bn != q.forced_bn) continue;
+    if (q.forced_bn <= 0) {
+      if (q.geglu && bn < 64) continue;
+      if (bn > 64 && q.N % bn != 0) continue;          // ragged N only with the narrow tiles
     }
-    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+    const long long tiles = static_cast<long long>(q.m_tiles) * ((q.N + bn - 1) / bn);
     for (int s = 1; s <= 16; ++s) {
       if (s > 1) {
-        if (split_req == 1 || geglu || ws_floats_avail <= 0) break;
-        if (num_kb / s < 6) break;
-        if (tiles > 16384 || tiles * s * 128LL * bn > ws_floats_avail) break;
+        if (q.split_req == 1 || q.geglu || q.ws_floats_avail <= 0) break;
+        if (q.num_kb / s < 6) break;
+        if (tiles > 16384 || tiles * s * 128LL * bn > q.ws_floats_avail) break;
+        if (tiles * (s - 1) >= 2LL * sms) break;       // already more than two CTAs per SM without it
       }
-      if (split_req > 1 && s != split_req) continue;
-      const int kbs = (num_kb + s - 1) / s;
-      if (static_cast<long long>(kbs) * (s - 1) >= num_kb) continue;   // an empty split
+      if (q.split_req > 1 && s != q.split_req) continue;
+      const int kbs = (q.num_kb + s - 1) / s;
+      if (static_cast<long long>(kbs) * (s - 1) >= q.num_kb) continue;   // an empty split
       const long long ctas = tiles * s;
-      const double waves = static_cast<double>((ctas + sms - 1) / sms);
-      // measured on B200: ~3 cycles per byte-row of L2 feed per k-block, ~2000 cycles per 32-column
-      // epilogue chunk (half hidden when a second CTA shares the SM), ~1500 fixed
-      const double main = kbs * 3.05 * (128 + bn);
-      double epi = 65.0 * bn;
+      const bool wide = ctas <= sms;                       // one CTA per SM, 8 epilogue warps
+      const bool two = !wide && (bn <= 160 || pair);       // 4 epilogue warps, two CTAs per SM
+      const int ksub = plan_ksub(bn, pair, wide);
+      double ovh = ksub == 2 ? 290.0 : 520.0;
+      if (pair) ovh *= 0.92;
+      const double mma = 2.0 * bn;
+      const long long slots = static_cast<long long>(sms) * (two ? 2 : 1);
+      const double waves = static_cast<double>((ctas + slots - 1) / slots);
+      double conc = 1.0;                                   // CTAs sharing one tensor pipe
+      if (two) conc = ctas >= 2LL * sms ? 2.0 : static_cast<double>(ctas) / sms;
+      const double iters = static_cast<double>((kbs + ksub - 1) / ksub) * ksub;
+      const double main = iters * (ovh > conc * mma ? ovh : conc * mma);
+      double epi = two ? 500.0 + 55.0 * bn : 1500.0 + 28.0 * bn;
       if (s > 1) epi += 30.0 * bn + 6.0 * bn * s;
-      const bool shared_sm = ctas > sms && bn <= 160;
-      const double cost = waves * (1500.0 + main + (shared_sm ? 0.5 : 1.0) * epi);
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = TilePlan{bn, s, kbs}; }
+      if (two) epi *= 0.5;
+      f(TilePlan{bn, s, kbs, pair}, waves * (2500.0 + (pair ? 900.0 : 0.0) + main + epi));
     }
   }
+}
+
+TilePlan pick_plan(const PlanQuery& q) {
+  TilePlan best{64, 1, q.num_kb, 0};
+  double best_cost = -1.0;
+  for_each_plan(q, [&](const TilePlan& t, double cost) {
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = t; }
+  });
   return best;
+}
+
+// ---- plan cache + on-device autotuning ---------------------------------------------------------
+// The first dbir_gemm call for a problem signature outside stream capture times every plan the model
+// rates within 3x of its best (cold L2: the real layers stream their weights from HBM) on the
+// caller's own operands, with the outputs redirected to scratch, and caches the winner. Split-K
+// factors change the fp32 summation order, so results can differ at rounding level between
+// processes; DBIR_GEMM_AUTOTUNE=0 keeps the deterministic model choice.
+using PlanKey = std::array<long long, 20>;
+std::mutex g_plan_mu;
+std::map<PlanKey, TilePlan> g_plan_cache;
+int g_tuned_problems = 0;
+
+bool autotune_enabled() {
+  static const int on = [] { const char* e = getenv("DBIR_GEMM_AUTOTUNE"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+
+PlanKey make_key(const dbir_gemm_args* a) {
+  PlanKey k{};
+  int i = 0;
+  k[i++] = a->M; k[i++] = a->N; k[i++] = a->K; k[i++] = a->a_mode;
+  k[i++] = a->img_n; k[i++] = a->img_h; k[i++] = a->img_w; k[i++] = a->img_c; k[i++] = a->ksize;
+  k[i++] = a->out_kind; k[i++] = a->geglu; k[i++] = a->force_bn; k[i++] = a->split_k; k[i++] = a->cta_pair;
+  k[i++] = a->residual != nullptr; k[i++] = a->gn_partials != nullptr;
+  k[i++] = a->splitk_ws ? a->splitk_ws_bytes : 0;
+  k[i++] = a->lda; k[i++] = a->ldo; k[i++] = a->act;
+  return k;
+}
+
+int gemm_impl(const dbir_gemm_args* a, cudaStream_t st, const TilePlan* forced);
+
+struct TuneScratch {
+  void* out = nullptr; size_t out_cap = 0;
+  void* part = nullptr; size_t part_cap = 0;
+  void* flush = nullptr;
+  static constexpr size_t FLUSH_BYTES = 192u << 20;     // > the 126 MB L2
+  cudaEvent_t ev[3][2] = {};
+  bool ready = false;
+};
+TuneScratch g_ts;
+
+bool tune_reserve(void** ptr, size_t* cap, size_t need) {
+  if (need <= *cap) return true;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *cap = 0;
+  if (cudaMalloc(ptr, need) != cudaSuccess) { cudaGetLastError(); return false; }
+  *cap = need;
+  return true;
+}
+
+// Returns true and the fastest measured plan, or false if tuning could not run (keeps the model's plan).
+bool tune_plan(const dbir_gemm_args* a, cudaStream_t st, const PlanQuery& q, TilePlan* out_plan) {
+  TuneScratch& ts = g_ts;
+  if (!ts.ready) {
+    if (cudaMalloc(&ts.flush, TuneScratch::FLUSH_BYTES) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (auto& e : ts.ev) for (auto& x : e) if (cudaEventCreate(&x) != cudaSuccess) return false;
+    ts.ready = true;
+  }
+  const int eb = a->out_kind == 0 ? 4 : 2;
+  const size_t out_bytes = static_cast<size_t>(a->M) * a->ldo * eb;
+  if (!tune_reserve(&ts.out, &ts.out_cap, out_bytes)) return false;
+  dbir_gemm_args t = *a;
+  t.out = ts.out;
+  t.debug_stamps = nullptr;
+  t.prefetch_ptr = nullptr; t.prefetch_bytes = 0;
+  if (a->gn_partials) {
+    const long long imgs = a->a_mode == 1 ? a->img_n : a->M / a->gn_rows_per_img;
+    const long long slots = a->a_mode == 1 ? dbir_gemm_gn_slots(a->img_h, a->img_w, 0)
+                                           : dbir_gemm_gn_slots(0, 0, a->gn_rows_per_img);
+    if (slots <= 0 || !tune_reserve(&ts.part, &ts.part_cap, static_cast<size_t>(imgs) * slots * a->N * 8)) return false;
+    t.gn_partials = ts.part;
+  }
+  std::vector<std::pair<double, TilePlan>> cands;
+  double best_model = -1.0;
+  for_each_plan(q, [&](const TilePlan& p, double c) {
+    cands.emplace_back(c, p);
+    if (best_model < 0 || c < best_model) best_model = c;
+  });
+  float best_ms = -1.f;
+  for (const auto& c : cands) {
+    if (c.first > 3.0 * best_model) continue;
+    if (gemm_impl(&t, st, &c.second) != 0) continue;              // warm-up (also validates the plan)
+    bool ok = true;
+    for (int r = 0; r < 3 && ok; ++r) {
+      ok = cudaMemsetAsync(ts.flush, r, TuneScratch::FLUSH_BYTES, st) == cudaSuccess &&
+           cudaEventRecord(ts.ev[r][0], st) == cudaSuccess && gemm_impl(&t, st, &c.second) == 0 &&
+           cudaEventRecord(ts.ev[r][1], st) == cudaSuccess;
+    }
+    if (!ok || cudaEventSynchronize(ts.ev[2][1]) != cudaSuccess) { cudaGetLastError(); continue; }
+    float ms = -1.f;
+    for (int r = 0; r < 3; ++r) {
+      float x = 0.f;
+      if (cudaEventElapsedTime(&x, ts.ev[r][0], ts.ev[r][1]) == cudaSuccess && (ms < 0 || x < ms)) ms = x;
+    }
+    if (ms > 0 && (best_ms < 0 || ms < best_ms)) { best_ms = ms; *out_plan = c.second; }
+  }
+  return best_ms > 0;
+}
+
+TilePlan choose_plan(const dbir_gemm_args* a, cudaStream_t st, const PlanQuery& q) {
+  if (!autotune_enabled()) return pick_plan(q);
+  const PlanKey key = make_key(a);
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto it = g_plan_cache.find(key);
+    if (it != g_plan_cache.end()) return it->second;
+  }
+  TilePlan plan = pick_plan(q);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return plan; }
+  if (cs != cudaStreamCaptureStatusNone) return plan;       // cannot time inside a capture: model plan, not cached
+  TilePlan tuned = plan;
+  if (tune_plan(a, st, q, &tuned)) plan = tuned;
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_plan_cache[key] = plan;
+  ++g_tuned_problems;
+  return plan;
 }
 
 }  // namespace
 
 extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return gemm_impl(a, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+/* Number of problem signatures tuned so far / drop every cached plan (tests, A/B runs). */
+extern "C" int32_t dbir_gemm_tuned_problems(void) { return g_tuned_problems; }
+extern "C" void dbir_gemm_clear_plans(void) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_plan_cache.clear();
+}
+
+namespace {
+int gemm_impl(const dbir_gemm_args* a, cudaStream_t st, const TilePlan* forced) {
   DBIR_REQUIRE(a != nullptr, "dbir_gemm: null args");
   DBIR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "dbir_gemm: bad shape M=%d N=%d K=%d", a->M,
                a->N, a->K);
@@ -695,7 +946,8 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
   }
   constexpr long long TICKET_FLOATS = 16384;
   const long long ws_floats = a->splitk_ws ? a->splitk_ws_bytes / 4 - TICKET_FLOATS : 0;
-  const TilePlan plan = pick_plan(m_tiles, a->N, p.num_kb, a->geglu, a->force_bn, a->split_k, ws_floats);
+  const PlanQuery pq{m_tiles, a->N, p.num_kb, a->geglu, a->force_bn, a->split_k, a->cta_pair, ws_floats};
+  const TilePlan plan = forced ? *forced : choose_plan(a, st, pq);
   const int bn = plan.bn;
   p.splits = plan.splits;
   p.kb_per_split = plan.kb_per_split;
@@ -707,7 +959,7 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
     const long long ldb = a->ldb > 0 ? a->ldb : a->K;
     uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ldb) * 2};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(plan.pair ? bn / 2 : bn)};
     if (dbir_make_tmap(&tb, a->b, 2, dims, strides, box, 2, 1)) return -3;
   }
   dim3 grid(m_tiles, (a->N + bn - 1) / bn, plan.splits);
@@ -715,17 +967,31 @@ extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
   static const int wide_mode = [] { const char* e = getenv("DBIR_GEMM_WIDE"); return e ? atoi(e) : -1; }();
   const bool wide = wide_mode >= 0 ? wide_mode != 0
                                    : static_cast<long long>(grid.x) * grid.y * grid.z <= dbir_sm_count();
+  // <BN, STAGES, EW, PAIR, KSUB>: EW == 4 kernels run two CTAs per SM (<= ~104 KB of stages each)
+#define DBIR_GO(BN_, ST_, EW_, PAIR_, KS_) return launch<BN_, ST_, EW_, PAIR_, KS_>(ta, tb, to, tr, p, grid, st)
+  if (plan.pair) {
+    switch (bn) {
+      case 64:  if (wide) DBIR_GO(64, 4, 8, true, 2);  else DBIR_GO(64, 2, 4, true, 2);
+      case 128: if (wide) DBIR_GO(128, 4, 8, true, 2); else DBIR_GO(128, 2, 4, true, 2);
+      case 160: if (wide) DBIR_GO(160, 4, 8, true, 2); else DBIR_GO(160, 2, 4, true, 2);
+      case 256: if (wide) DBIR_GO(256, 3, 8, true, 2); else DBIR_GO(256, 3, 4, true, 1);
+      default:
+        dbir_set_error("dbir_gemm: unsupported paired tile width %d", bn);
+        return -2;
+    }
+  }
   switch (bn) {
-    case 32:  return wide ? launch<32, 7, 8>(ta, tb, to, tr, p, grid, st) : launch<32, 5, 4>(ta, tb, to, tr, p, grid, st);
-    case 64:  return wide ? launch<64, 6, 8>(ta, tb, to, tr, p, grid, st) : launch<64, 4, 4>(ta, tb, to, tr, p, grid, st);
-    case 128: return wide ? launch<128, 4, 8>(ta, tb, to, tr, p, grid, st) : launch<128, 3, 4>(ta, tb, to, tr, p, grid, st);
-    case 160: return wide ? launch<160, 4, 8>(ta, tb, to, tr, p, grid, st) : launch<160, 3, 4>(ta, tb, to, tr, p, grid, st);
-    case 256: return wide ? launch<256, 4, 8>(ta, tb, to, tr, p, grid, st) : launch<256, 4, 4>(ta, tb, to, tr, p, grid, st);
+    case 32:  if (wide) DBIR_GO(32, 4, 8, false, 2);  else DBIR_GO(32, 2, 4, false, 2);
+    case 64:  if (wide) DBIR_GO(64, 4, 8, false, 2);  else DBIR_GO(64, 2, 4, false, 2);
+    case 128: if (wide) DBIR_GO(128, 3, 8, false, 2); else DBIR_GO(128, 3, 4, false, 1);
+    case 160: if (wide) DBIR_GO(160, 3, 8, false, 2); else DBIR_GO(160, 3, 4, false, 1);
+    case 256: DBIR_GO(256, 4, 8, false, 1);
     default:
       dbir_set_error("dbir_gemm: unsupported tile width %d", bn);
       return -2;
   }
 }
+}  // namespace
 
 extern "C" int32_t dbir_gemm_gn_slots(int32_t conv_h, int32_t conv_w, int32_t rows_per_img) {
   if (conv_h > 0 && conv_w > 0) {

@@ -35,7 +35,7 @@ class GemmArgs(C.Structure):
         ("bias_per_row", C.c_int32), ("reserved0", C.c_int32),
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
-        ("split_k", C.c_int32), ("reserved1", C.c_int32),
+        ("split_k", C.c_int32), ("cta_pair", C.c_int32),
         ("debug_stamps", C.c_void_p),
         ("gn_partials", C.c_void_p), ("gn_rows_per_img", C.c_int32), ("reserved2", C.c_int32),
         ("prefetch_ptr", C.c_void_p), ("prefetch_bytes", C.c_int64),
@@ -141,7 +141,7 @@ ACT = {None: 0, "none": 0, "gelu": 1, "lrelu": 2, "silu": 3}
 def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual=None,
          lda=0, ldb=0, ldo=None, ldr=None, conv=None, act=None, act_param=0.0, alpha=1.0,
          geglu=False, force_bn=0, bias_per_row=False, out2=None, ldo2=None, splitk_ws=None,
-         split_k=0, debug_stamps=None, gn_partials=None, gn_rows_per_img=0, prefetch=None):
+         split_k=0, cta_pair=0, debug_stamps=None, gn_partials=None, gn_rows_per_img=0, prefetch=None):
     """out = residual + alpha * act(A @ B^T + bias + rowvec). conv = (n, h, w, c, ksize)."""
     lib = load()
     g = GemmArgs()
@@ -171,6 +171,7 @@ def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual
         g.splitk_ws = splitk_ws.data_ptr()
         g.splitk_ws_bytes = splitk_ws.numel() * splitk_ws.element_size()
     g.split_k = split_k
+    g.cta_pair = cta_pair
     g.debug_stamps = _ptr(debug_stamps)
     g.gn_partials = _ptr(gn_partials)
     g.gn_rows_per_img = gn_rows_per_img
@@ -210,6 +211,15 @@ def gn_workspace_floats(n, hw, c) -> int:
     lib = load()
     lib.dbir_gn_workspace_floats.restype = C.c_int64
     return int(lib.dbir_gn_workspace_floats(n, hw, c))
+
+
+def gemm_tuned_problems() -> int:
+    """Problem signatures dbir_gemm has planned (autotuned) so far."""
+    return int(load().dbir_gemm_tuned_problems())
+
+
+def gemm_clear_plans() -> None:
+    load().dbir_gemm_clear_plans()
 
 
 def gemm_gn_slots(conv_h=0, conv_w=0, rows_per_img=0) -> int:

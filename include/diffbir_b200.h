@@ -61,7 +61,7 @@ typedef struct dbir_gemm_args {
                            partial tiles); NULL disables split-K. Summation order is fixed. */
   int64_t splitk_ws_bytes;
   int32_t split_k;      /* 0 = auto, 1 = off, n > 1 = force n splits */
-  int32_t reserved1;
+  int32_t cta_pair;     /* CTA pairs (cta_group::2, M=256 MMAs): 0 = auto, 1 = whenever the tile count is even, 2 = never */
   void* debug_stamps;   /* optional int64 [ctas][8] clock64 stamps (start, setup, acc ready, end) */
   void* gn_partials;    /* optional fp32 [img][dbir_gemm_gn_slots()][N][2]: per 32-row-slot column sums and
                            sums of squares of the OUTPUT (fused GroupNorm statistics; see dbir_gn_finalize) */
@@ -73,6 +73,12 @@ typedef struct dbir_gemm_args {
 /* Number of 32-row slots per image dbir_gemm writes into gn_partials (conv: h, w > 0; matrix: rows_per_img). */
 int32_t dbir_gemm_gn_slots(int32_t conv_h, int32_t conv_w, int32_t rows_per_img);
 int dbir_gemm(const dbir_gemm_args* args, void* stream);
+/* dbir_gemm keeps a plan (tile width, CTA pairing, split-K) per problem signature. The first call
+ * for a signature made outside stream capture times the candidate plans on the caller's operands
+ * (outputs redirected to scratch, cold L2) and caches the fastest; DBIR_GEMM_AUTOTUNE=0 selects
+ * the analytic model instead (bit-reproducible across processes: split-K changes summation order). */
+int32_t dbir_gemm_tuned_problems(void);   /* signatures planned so far */
+void dbir_gemm_clear_plans(void);         /* forget every cached plan */
 
 /* ---- flash attention, head_dim 64 (tcgen05) ------------------------------------------
  * out[b, i, h*64 + :] = softmax_j(q_h[i] . k_h[j] / 8) v_h[j]; q/k/v/out are op16 matrices

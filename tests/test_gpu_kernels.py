@@ -256,6 +256,73 @@ def test_sampler_step_and_tiles_bit_exact(L, golden_dir):
     assert torch.equal(blended, acc / cnt)
 
 
+@pytest.mark.parametrize("M,N,K,fbn", [(256, 64, 64, 64), (512, 1280, 1280, 0), (2048, 640, 2560, 0),
+                                         (8192, 320, 320, 0), (4000, 320, 320, 160), (1024, 200, 448, 64),
+                                         (2048, 1280, 640, 256)])
+def test_gemm_cta_pair_plain(L, M, N, K, fbn):
+    """cta_group::2 path (M=256 MMAs over a 2-CTA cluster): same fp32 result as the single-CTA
+    path up to accumulation order (identical here: same k order), and vs the fp32 reference."""
+    dt = L.operand_dtype()
+    a, b = rnd(M, K, seed=1).to(dt), rnd(N, K, seed=2, scale=K ** -0.5).to(dt)
+    bias, res = rnd(N, seed=3), rnd(M, N, seed=4)
+    o1, o2 = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    L.gemm(a, b, o1, M=M, N=N, K=K, bias=bias, residual=res, force_bn=fbn, alpha=0.7, cta_pair=1, split_k=1)
+    L.gemm(a, b, o2, M=M, N=N, K=K, bias=bias, residual=res, force_bn=fbn, alpha=0.7, cta_pair=2, split_k=1)
+    ref = 0.7 * (a.float() @ b.float().t() + bias) + res
+    assert rel_err(o1, ref) < 2e-5
+    assert torch.equal(o1, o2)
+    o16 = torch.empty(M, N, device="cuda", dtype=dt)
+    L.gemm(a, b, o16, M=M, N=N, K=K, bias=bias, act="gelu", force_bn=fbn, cta_pair=1)
+    assert rel_err(o16, F.gelu(a.float() @ b.float().t() + bias)) < tol16(L)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,fbn,split", [(2, 64, 64, 320, 320, 0, 0), (2, 16, 16, 1280, 1280, 0, 0),
+                                                       (2, 32, 32, 640, 640, 128, 0), (2, 32, 32, 1920, 640, 256, 0),
+                                                       (2, 16, 16, 1280, 1280, 128, 3), (1, 40, 72, 128, 192, 64, 0)])
+def test_gemm_cta_pair_conv(L, n, h, w, cin, cout, fbn, split):
+    dt = L.operand_dtype()
+    x = rnd(n, h, w, cin, seed=1).to(dt)
+    wt = rnd(cout, cin, 3, 3, seed=2, scale=(cin * 9) ** -0.5).to(dt)
+    bias, rv = rnd(cout, seed=3), rnd(n, cout, seed=4)
+    res = rnd(n * h * w, cout, seed=5)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    ws = torch.zeros(16 * 1024 * 1024 + 16384, device="cuda")
+    slots = L.gemm_gn_slots(conv_h=h, conv_w=w)
+    outs, parts = [], []
+    for pair in (1, 2):
+        out = torch.empty(n * h * w, cout, device="cuda")
+        part = torch.zeros(n, slots, cout, 2, device="cuda")
+        L.gemm(x, wp, out, M=n * h * w, N=cout, K=9 * cin, bias=bias, rowvec=rv, residual=res,
+               conv=(n, h, w, cin, 3), force_bn=fbn, splitk_ws=ws, split_k=split if split else 1,
+               gn_partials=part, cta_pair=pair)
+        outs.append(out)
+        parts.append(part)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1) + rv[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(n * h * w, cout) + res
+    assert rel_err(outs[0], ref) < 3e-5
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(parts[0], parts[1])
+    assert (ws[:16384] == 0).all()
+
+
+def test_gemm_cta_pair_geglu(L):
+    from diffbir_b200.engine.common import pack_geglu
+    dt = L.operand_dtype()
+    M, C, fbn = 2048, 640, 128
+    inner = 4 * C
+    a = rnd(M, C, seed=1).to(dt)
+    w = rnd(2 * inner, C, seed=2, scale=C ** -0.5)
+    bias = rnd(2 * inner, seed=3)
+    wp, bp = pack_geglu(w, bias, fbn, "cuda")
+    o1 = torch.empty(M, inner, device="cuda", dtype=dt)
+    o2 = torch.empty(M, inner, device="cuda", dtype=dt)
+    L.gemm(a, wp, o1, M=M, N=2 * inner, K=C, bias=bp, geglu=True, force_bn=fbn, cta_pair=1)
+    L.gemm(a, wp, o2, M=M, N=2 * inner, K=C, bias=bp, geglu=True, force_bn=fbn, cta_pair=2)
+    hcat = a.float() @ w.to(dt).float().t() + bias
+    assert rel_err(o1, hcat[:, :inner] * F.gelu(hcat[:, inner:])) < tol16(L)
+    assert torch.equal(o1, o2)
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,split", [(2, 8, 8, 1280, 1280, 0), (2, 8, 8, 1280, 1280, 7),
                                                    (2, 16, 16, 1280, 1280, 3), (1, 8, 8, 2560, 1280, 0)])
 def test_gemm_split_k_deterministic(L, n, h, w, cin, cout, split):
