@@ -308,8 +308,10 @@ class CldmEngine:
         qkv = ws.get(tag + ":at_qkv", (M, 3 * c), self.op_dtype)
         self._gemm(tag, a16, W[q + "qkv.w"], qkv, M=M, N=3 * c, K=c)
         att = ws.get(tag + ":at_o16", (M, c), self.op_dtype)
+        nws = lib.attention_ws_bytes(nb, heads, hw, hw)
+        aws = ws.get(tag + ":at_sk", (nws // 4,), torch.float32, zero=True) if nws else None
         lib.attention(qkv, qkv[:, c:], qkv[:, 2 * c:], att, batch=nb, heads=heads, sq=hw, skv=hw,
-                      ldq=3 * c, ldk=3 * c, ldv=3 * c, ldo=c)
+                      ldq=3 * c, ldk=3 * c, ldv=3 * c, ldo=c, ws=aws)
         self._gemm(tag, att, W[q + "o1.w"], t, M=M, N=c, K=c, bias=W[q + "o1.b"], residual=t)
         # cross-attention on the (pre-projected) text context
         lib.layernorm(t, c, M, c, W[q + "norm2.weight"], W[q + "norm2.bias"], a16, c)

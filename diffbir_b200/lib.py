@@ -194,12 +194,23 @@ def _fp(t):
     return C.c_void_p(None if t is None else t.data_ptr())
 
 
-def attention(q, k, v, out, *, batch, heads, sq, skv, ldq, ldk, ldv, ldo):
-    """Flash attention, head_dim 64; q/k/v/out are op16 tensors (possibly column slices)."""
+def attention_ws_bytes(batch, heads, sq, skv) -> int:
+    """Bytes of (zero-initialised, per-stream) workspace that let dbir_attention_sk balance this
+    shape over all SMs; 0 when whole tiles per CTA are used anyway."""
+    lib = load()
+    lib.dbir_attention_ws_bytes.restype = C.c_int64
+    return int(lib.dbir_attention_ws_bytes(batch, heads, sq, skv))
+
+
+def attention(q, k, v, out, *, batch, heads, sq, skv, ldq, ldk, ldv, ldo, ws=None):
+    """Flash attention, head_dim 64; q/k/v/out are op16 tensors (possibly column slices).
+    ws: optional zero-initialised uint8/float32 scratch of attention_ws_bytes() bytes."""
+    ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
+
     def call():
-        check(load().dbir_attention(_fp(q), _fp(k), _fp(v), _fp(out), batch, heads, sq, skv,
-                                    C.c_int64(ldq), C.c_int64(ldk), C.c_int64(ldv), C.c_int64(ldo),
-                                    _sp()), "dbir_attention")
+        check(load().dbir_attention_sk(_fp(q), _fp(k), _fp(v), _fp(out), batch, heads, sq, skv,
+                                       C.c_int64(ldq), C.c_int64(ldk), C.c_int64(ldv), C.c_int64(ldo),
+                                       _fp(ws), C.c_int64(ws_bytes), _sp()), "dbir_attention_sk")
     with _Prof("attention", (batch, heads, sq, skv), 4.0 * batch * heads * sq * skv * 64):
         call()
     if _record is not None:

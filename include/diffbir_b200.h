@@ -89,6 +89,15 @@ void dbir_gemm_clear_plans(void);         /* forget every cached plan */
 int dbir_attention(const void* q, const void* k, const void* v, void* out, int32_t batch,
                    int32_t heads, int32_t sq, int32_t skv, int64_t ldq, int64_t ldk, int64_t ldv,
                    int64_t ldo, void* stream);
+/* Same, with an optional workspace that enables the stream-K decomposition: when whole 128-query
+ * tiles would leave the last wave of CTA slots (two per SM) mostly idle, every CTA instead takes an
+ * equal share of the (tile, 64-key step) space and tiles cut by a CTA boundary are combined through
+ * `ws` (fixed part order: deterministic). ws: dbir_attention_ws_bytes() bytes, zero-initialised once
+ * by the caller, private to one stream; NULL / too small = whole tiles per CTA. */
+int dbir_attention_sk(const void* q, const void* k, const void* v, void* out, int32_t batch,
+                      int32_t heads, int32_t sq, int32_t skv, int64_t ldq, int64_t ldk,
+                      int64_t ldv, int64_t ldo, void* ws, int64_t ws_bytes, void* stream);
+int64_t dbir_attention_ws_bytes(int32_t batch, int32_t heads, int32_t sq, int32_t skv);  /* 0: not needed */
 
 /* ---- GroupNorm (32 groups) / LayerNorm ------------------------------------------------
  * dbir_gn_stats: per-(image, group) mean and rstd of the virtual concat [src1 | src2] (fp32
@@ -177,6 +186,12 @@ int dbir_tile_gather(const float* full, int32_t b, int32_t c, int32_t h, int32_t
 int dbir_tile_blend(const float* tiles, int32_t b, int32_t c, int32_t h, int32_t w,
                     const int32_t* coords, int32_t ntiles, int32_t tile, const float* weights,
                     float* out, void* stream);
+
+/* ---- calibration probe (not part of the product path) ------------------------------------
+ * Cycles for `iters` back-to-back 128 x n x 16 tcgen05 MMAs (one CTA) into out_cycles[0] (int64). */
+void dbir_debug_attn_stamps(void* buf);   /* per-CTA clock64 sums of later attention launches -> buf [ctas][8] int64; NULL = off */
+int dbir_debug_mma_rate(int32_t n, int32_t b_mn_major, int32_t iters, int32_t a_in_tmem, void* out_cycles,
+                        void* stream);
 
 #ifdef __cplusplus
 }

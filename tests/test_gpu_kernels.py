@@ -124,6 +124,18 @@ def test_attention(L, b, heads, sq, skv):
     ref = F.scaled_dot_product_attention(split(q, sq), split(k, skv), split(v, skv))
     ref = ref.permute(0, 2, 1, 3).reshape(b * sq, c)
     assert rel_err(out, ref) < 2 * tol16(L)
+    # stream-K decomposition (tiles cut by CTA boundaries are combined through a workspace):
+    # same result up to the combine's rounding, bit-identical across runs, tickets self-reset
+    nws = L.attention_ws_bytes(b, heads, sq, skv)
+    assert (nws > 0) == ((b, heads, sq, skv) == (2, 5, 4096, 4096))
+    if nws:
+        ws = torch.zeros(nws // 4, device="cuda")
+        o1, o2 = torch.empty_like(out), torch.empty_like(out)
+        for o in (o1, o2):
+            L.attention(q, k, v, o, batch=b, heads=heads, sq=sq, skv=skv, ldq=ldq, ldk=ldk, ldv=ldv, ldo=c, ws=ws)
+        assert rel_err(o1, ref) < 2 * tol16(L)
+        assert torch.equal(o1, o2)
+        assert (ws[:16384] == 0).all()
 
 
 @pytest.mark.parametrize("n,h,w,c1,c2", [(2, 64, 64, 320, 0), (2, 16, 16, 1280, 640), (2, 32, 32, 640, 320),

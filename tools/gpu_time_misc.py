@@ -41,7 +41,9 @@ for b, h, sq, skv, cnt in [(2, 5, 4096, 4096, 7), (2, 10, 1024, 1024, 7), (2, 20
         kv = torch.randn(b * skv, 2 * c, device=dev).to(dt)
         k, v, ldq, ldk = kv, kv[:, c:], c, 2 * c
     out = torch.empty(b * sq, c, device=dev, dtype=dt)
-    us = timeit(lambda: lib.attention(q, k, v, out, batch=b, heads=h, sq=sq, skv=skv, ldq=ldq, ldk=ldk, ldv=ldk, ldo=c))
+    nws = lib.attention_ws_bytes(b, h, sq, skv)
+    aws = torch.zeros(nws // 4, device=dev) if nws else None
+    us = timeit(lambda: lib.attention(q, k, v, out, batch=b, heads=h, sq=sq, skv=skv, ldq=ldq, ldk=ldk, ldv=ldk, ldo=c, ws=aws))
     tot += us * cnt
     print(f"attention b={b} h={h:2d} sq={sq:4d} skv={skv:4d} x{cnt}: {us:7.1f} us  {4.0 * b * h * sq * skv * 64 / us / 1e6:6.1f} TFLOP/s")
 print(f"attention weighted total per forward: {tot / 1e3:.2f} ms")
