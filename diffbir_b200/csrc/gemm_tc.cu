@@ -153,9 +153,21 @@ __device__ __forceinline__ void epi_issue_residual(const GemmParams& p, EpiCtx& 
 // whose residual tile can start loading into the buffer this chunk frees.
 __device__ __forceinline__ void finish_chunk(const GemmParams& p, EpiCtx& e, float* v, int lane, int chunk_idx,
                                              int gc0, int ncols, int next_gc0, long long out_row, int vec_idx,
-                                             bool raw_math) {
+                                             bool raw_math, bool have_pre = false, float pre = 0.f) {
   const int b = chunk_idx & 1;
-  if (raw_math) {
+  if (raw_math && have_pre) {
+    // bias + row vector of this chunk were fetched while the mainloop ran (lane == column)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, pre, j);
+    if (p.act) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.act_param);
+    }
+    if (p.alpha != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+    }
+  } else if (raw_math) {
     if (p.bias) {
       if (p.bias_per_row) {
         const float bv = out_row >= 0 ? __ldg(p.bias + out_row) : 0.f;
@@ -473,6 +485,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (long long off = me * 128; off < p.pf_bytes; off += nthr * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf_ptr + off));
     }
+    // Per-column addends (bias + the row vector of this warp's image) of every chunk this warp will
+    // finish, fetched now so that their L2 latency hides behind the mainloop: lane == column, one
+    // register per chunk. Needs one row vector for the whole warp (images of >= 32 rows).
+    constexpr int MAX_PRE = BN / CSTEP + 1;
+    float pre[MAX_PRE];
+    bool have_pre = false;
+    if (!p.geglu && !p.bias_per_row && (p.bias || p.rowvec)) {
+      const bool any_row = __any_sync(0xffffffffu, out_row >= 0);
+      // masked lanes of lane 0 would make v0 meaningless: take the vector of the first valid row
+      const unsigned vm = __ballot_sync(0xffffffffu, out_row >= 0);
+      const int vsel = any_row ? __shfl_sync(0xffffffffu, vec_idx, __ffs(vm) - 1) : 0;
+      const bool uniform = !p.rowvec || !any_row || __all_sync(0xffffffffu, out_row < 0 || vec_idx == vsel);
+      if (uniform) {
+        have_pre = true;
+#pragma unroll
+        for (int i = 0; i < MAX_PRE; ++i) {
+          const int col = n_tile * BN + c_first + i * CSTEP + lane;
+          float x = 0.f;
+          if (c_first + i * CSTEP < BN && col < p.N) {
+            if (p.bias) x = __ldg(p.bias + col);
+            if (p.rowvec && any_row) x += __ldg(p.rowvec + static_cast<long long>(vsel) * p.N + col);
+          }
+          pre[i] = x;
+        }
+      }
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     if (p.dbg) t_acc = clock64();
@@ -513,7 +551,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-        finish_chunk(p, e, v, lane, ci, gc0, ncols, (c0 + 2 * CSTEP < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true);
+        finish_chunk(p, e, v, lane, ci, gc0, ncols, (c0 + 2 * CSTEP < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true,
+                     have_pre, pre[(c0 - c_first) / CSTEP]);
         ++ci;
       }
       if (p.splits > 1) {
@@ -550,7 +589,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += __ldcg(wcol + j * BM);
             }
-            finish_chunk(p, e, v, lane, cj, gc0, ncols, (c0 + 2 * CSTEP < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true);
+            finish_chunk(p, e, v, lane, cj, gc0, ncols, (c0 + 2 * CSTEP < BN && ngc < p.N) ? ngc : -1, out_row, vec_idx, true,
+                         have_pre, pre[(c0 - c_first) / CSTEP]);
             ++cj;
           }
         }

@@ -22,7 +22,7 @@ extern "C" const char* dbir_version(void) {
 }
 extern "C" int dbir_operand_kind(void) { return DBIR_OPERAND_KIND; }
 extern "C" int dbir_pdl_enabled(void) {
-  static const int on = [] { const char* e = getenv("DBIR_PDL"); return e ? atoi(e) : 0; }();
+  static const int on = [] { const char* e = getenv("DBIR_PDL"); return e ? atoi(e) : 1; }();
   return on;
 }
 
