@@ -266,10 +266,12 @@ def run_ours(args):
     n0 = lib.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.nvtx.range_push("dbir_timed")      # ncu --nvtx --nvtx-include "dbir_timed/" profiles exactly this region
     e0.record()
     for _ in range(args.steps):
         one(True)
     e1.record()
+    torch.cuda.nvtx.range_pop()
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = lib.launches() - n0

@@ -662,7 +662,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, 
 }
 
 // Tile width, CTA pairing and split-K factor from a cost model in SM cycles, calibrated on B200
-// with the per-CTA clock64 stamps (tools/gpu_pair_timeline.py, profiles/r01_gemm_mainloop.txt):
+// with the per-CTA clock64 stamps (tools/gpu_pair_timeline.py, profiles/r01_probes.txt):
 //   * one 64-wide k-block costs max(MMA time, loop overhead): the MMAs take ~2*BN cycles
 //     (128 x BN x 64 at 128 x 256 x 16 per 128 cycles), the producer / issue loops ~520 cycles per
 //     stage iteration (barrier, TMA-issue and commit latencies) -> ~290 per k-block with two
