@@ -1,0 +1,7 @@
+"""diffbir.inference counterpart: the inference loops whose networks are on the accelerated path.
+BID (SCUNet cleaner), unaligned faces (face detector) and custom loops are refused by the CLI."""
+from .bfr_loop import BFRInferenceLoop
+from .bsr_loop import BSRInferenceLoop
+from .loop import InferenceLoop
+
+__all__ = ["InferenceLoop", "BSRInferenceLoop", "BFRInferenceLoop"]
