@@ -1,5 +1,5 @@
 """Times dbir_gemm on the shapes of one ControlNet+UNet forward (batch 2, latent 64x64).
-   python tools/gpu_time_gemm.py        (DBIR_GEMM_DEEP=0/1 to force shallow/deep pipelines)"""
+   python tools/gpu_time_gemm.py        (DBIR_GEMM_PAIR=0|1, DBIR_GEMM_AUTOTUNE=0 to constrain the plans)"""
 import sys
 from pathlib import Path
 
