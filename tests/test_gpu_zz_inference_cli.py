@@ -1,4 +1,5 @@
-"""-m gpu: the inference.py command line end to end on synthetic weights (full SD-2.1 config):
+"""(named to run last under `pytest -x`)
+-m gpu: the inference.py command line end to end on synthetic weights (full SD-2.1 config):
 folder of LQ images -> BSRInferenceLoop -> SwinIRPipeline -> PNGs of upscale x the input size."""
 import sys
 from pathlib import Path
