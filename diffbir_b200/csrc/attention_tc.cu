@@ -443,7 +443,8 @@ int attn_plan(int batch, int heads, int sq, int skv, int* parts_max) {
   const long long slots = 2LL * dbir_sm_count();
   *parts_max = 0;
   static const int sk_mode = [] { const char* e = getenv("DBIR_ATTN_STREAMK"); return e ? atoi(e) : 1; }();
-  if (!sk_mode || n_steps < 8 || tiles * n_steps < slots * 4) return static_cast<int>(tiles);
+  // (the ticket array holds 16384 tiles; such grids are many waves deep and need no balancing)
+  if (!sk_mode || n_steps < 8 || tiles * n_steps < slots * 4 || tiles > 16384) return static_cast<int>(tiles);
   const long long waves = (tiles + slots - 1) / slots;
   // a single, partly filled wave is left alone: its CTAs mostly have an SM to themselves
   if (waves < 2 || static_cast<double>(tiles) / static_cast<double>(waves * slots) >= 0.8) return static_cast<int>(tiles);
@@ -484,7 +485,6 @@ extern "C" int dbir_attention_sk(const void* q, const void* k, const void* v, vo
   p.q_tiles = (sq + TQ - 1) / TQ;
   p.n_steps = (skv + TK - 1) / TK;
   const long long tiles = static_cast<long long>(batch) * heads * p.q_tiles;
-  DBIR_REQUIRE(tiles <= 16384 || !ws, "dbir_attention: too many tiles for the ticket array");
   DBIR_REQUIRE(tiles * ((skv + TK - 1) / TK) < (1LL << 30), "dbir_attention: problem too large");
   p.tiles = static_cast<int>(tiles);
   p.total_steps = tiles * p.n_steps;
