@@ -866,6 +866,15 @@ TilePlan choose_plan(const dbir_gemm_args* a, cudaStream_t st, const PlanQuery& 
 extern "C" int dbir_gemm(const dbir_gemm_args* a, void* stream) {
   return gemm_impl(a, reinterpret_cast<cudaStream_t>(stream), nullptr);
 }
+/* The analytic model's plan for a tile grid (host only, no launch): out[0..3] = BN, splits, k-blocks per
+ * split, CTA pair flag. Lets the CPU test suite check the planner's invariants. */
+extern "C" int dbir_gemm_model_plan(int32_t m_tiles, int32_t N, int32_t num_kb, int32_t geglu, int32_t force_bn,
+                                    int32_t split_k, int32_t cta_pair, int64_t ws_floats, int32_t* out) {
+  DBIR_REQUIRE(m_tiles > 0 && N > 0 && num_kb > 0 && out, "dbir_gemm_model_plan: bad arguments");
+  const TilePlan t = pick_plan(PlanQuery{m_tiles, N, num_kb, geglu, force_bn, split_k, cta_pair, ws_floats});
+  out[0] = t.bn; out[1] = t.splits; out[2] = t.kb_per_split; out[3] = t.pair;
+  return 0;
+}
 /* Number of problem signatures tuned so far / drop every cached plan (tests, A/B runs). */
 extern "C" int32_t dbir_gemm_tuned_problems(void) { return g_tuned_problems; }
 extern "C" void dbir_gemm_clear_plans(void) {

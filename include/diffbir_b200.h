@@ -78,6 +78,9 @@ int dbir_gemm(const dbir_gemm_args* args, void* stream);
  * (outputs redirected to scratch, cold L2) and caches the fastest; DBIR_GEMM_AUTOTUNE=0 selects
  * the analytic model instead (bit-reproducible across processes: split-K changes summation order). */
 int32_t dbir_gemm_tuned_problems(void);   /* signatures planned so far */
+/* the analytic model's plan for a tile grid, host only: out[0..3] = BN, splits, k-blocks per split, pair */
+int dbir_gemm_model_plan(int32_t m_tiles, int32_t N, int32_t num_kb, int32_t geglu, int32_t force_bn,
+                         int32_t split_k, int32_t cta_pair, int64_t ws_floats, int32_t* out);
 void dbir_gemm_clear_plans(void);         /* forget every cached plan */
 
 /* ---- flash attention, head_dim 64 (tcgen05) ------------------------------------------

@@ -126,3 +126,38 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "diffbir_b200").rglob("*.py"):
         txt = p.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt, p
+
+
+def test_gemm_planner_invariants():
+    """dbir_gemm's analytic tile planner (host code, no GPU): every plan is runnable by the kernel
+    family — known tile widths, no empty split, split-K only with scratch and enough k-blocks, CTA
+    pairs only over an even number of M tiles, forced choices honoured, deterministic."""
+    import ctypes as C
+    import itertools
+    from diffbir_b200 import lib
+    L = lib.load()
+    out = (C.c_int32 * 4)()
+
+    def plan(m_tiles, N, num_kb, geglu=0, fbn=0, split=0, pair=0, ws=16 * 1024 * 1024):
+        assert L.dbir_gemm_model_plan(m_tiles, N, num_kb, geglu, fbn, split, pair, C.c_int64(ws), out) == 0
+        return tuple(out)
+
+    for m_tiles, N, num_kb in itertools.product((1, 2, 3, 4, 16, 64, 65, 512), (24, 200, 320, 640, 1280, 2560, 10240),
+                                                (1, 5, 7, 20, 45, 180, 360)):
+        bn, splits, kbs, pair = plan(m_tiles, N, num_kb)
+        assert bn in (32, 64, 128, 160, 256)
+        assert bn <= 64 or N % bn == 0                       # ragged N only with the narrow tiles
+        assert 1 <= splits <= 16 and kbs * splits >= num_kb and kbs * (splits - 1) < num_kb
+        assert splits == 1 or (num_kb // splits >= 6 and m_tiles * -(-N // bn) * splits * 128 * bn <= 16 * 1024 * 1024)
+        assert pair in (0, 1) and (not pair or (m_tiles % 2 == 0 and bn >= 64))
+        assert plan(m_tiles, N, num_kb) == (bn, splits, kbs, pair)
+        assert plan(m_tiles, N, num_kb, ws=0)[1] == 1         # no scratch, no split-K
+        assert plan(m_tiles, N, num_kb, split=1)[1] == 1
+        assert plan(m_tiles, N, num_kb, pair=2)[3] == 0
+        if m_tiles % 2 == 0:
+            assert plan(m_tiles, N, num_kb, pair=1, fbn=64)[3] == 1
+        assert plan(m_tiles, N, num_kb, fbn=64)[0] == 64
+    # GEGLU tiles are at least 64 wide and never split
+    assert plan(64, 2560, 5, geglu=1, fbn=128)[:2] == (128, 1)
+    # long-K, single-tile-row layers (8x8 latents) are split over k
+    assert plan(1, 1280, 180)[1] > 1
