@@ -45,6 +45,32 @@ def gaussian_weights(tile_width: int, tile_height: int) -> np.ndarray:
     return np.outer(yp, xp)
 
 
+def make_tiled_fn(fn, size: int, stride: int, scale_type: str = "up", scale: int = 1, channel=None,
+                  weight: str = "gaussian", dtype=None, device=None, progress: bool = False):
+    """Image-tiling wrapper of utils/common.py:172-232: the first argument is cut into row-major
+    `size` x `size` windows (last one snapped to the border), `fn(tile) * w` and `w` are accumulated
+    in that order, the result is `out / count`. Weights are built in fp64 and cast to the output
+    dtype exactly like the reference; extra arguments get the window as hi/hi_end/wi/wi_end."""
+    def tiled_fn(x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        sc = (lambda n: int(n * scale)) if scale_type == "up" else (lambda n: int(n // scale))
+        b, c, h, w = x.size()
+        out_dtype, out_device = dtype or x.dtype, device or x.device
+        out = torch.zeros((b, channel or c, sc(h), sc(w)), dtype=out_dtype, device=out_device)
+        count = torch.zeros_like(out, dtype=torch.float32)
+        ws = sc(size)
+        wnp = gaussian_weights(ws, ws)[None, None] if weight == "gaussian" else np.ones((1, 1, ws, ws))
+        weights = torch.tensor(wnp, dtype=out_dtype, device=out_device)
+        for hi, hi_end, wi, wi_end in sliding_windows(h, w, size, stride):
+            oh, oh_end, ow, ow_end = map(sc, (hi, hi_end, wi, wi_end))
+            if len(args) or len(kwargs):
+                kwargs.update(dict(hi=hi, hi_end=hi_end, wi=wi, wi_end=wi_end))
+            out[..., oh:oh_end, ow:ow_end] += fn(x[..., hi:hi_end, wi:wi_end], *args, **kwargs) * weights
+            count[..., oh:oh_end, ow:ow_end] += weights
+        return out / count
+
+    return tiled_fn
+
+
 def wavelet_blur(image: torch.Tensor, radius: int) -> torch.Tensor:
     k = torch.tensor([[0.0625, 0.125, 0.0625], [0.125, 0.25, 0.125], [0.0625, 0.125, 0.0625]],
                      dtype=image.dtype, device=image.device)[None, None].repeat(3, 1, 1, 1)

@@ -206,6 +206,37 @@ def make_tiled_fn(model: Callable, size: int, stride: int) -> Callable:
     return tiled
 
 
+def make_tiled_image_fn(fn: Callable, size: int, stride: int) -> Callable:
+    """Image version (scale 1, Gaussian weights) of utils/common.py:172-232, as used by the tiled
+    stage-1 branch (pipeline.py:389-394): row-major windows, accumulate fn(tile) * w and w, divide."""
+    def tiled(x):
+        b, c, h, w = x.shape
+        out = torch.zeros_like(x)
+        count = torch.zeros_like(x, dtype=torch.float32)
+        wts = torch.tensor(gaussian_weights(size, size)[None, None], dtype=x.dtype, device=x.device)
+        for hi, he, wi, we in sliding_windows(h, w, size, stride):
+            out[..., hi:he, wi:we] += fn(x[..., hi:he, wi:we]) * wts
+            count[..., hi:he, wi:we] += wts
+        return out / count
+    return tiled
+
+
+def apply_cleaner(cleaner: Callable, lq, tiled: bool = False, tile_size: int = 512, tile_stride: int = 256):
+    """SwinIRPipeline.apply_cleaner — pipeline.py:371-397 (both branches, the reference's order of
+    resize and network in each)."""
+    if tiled and (lq.shape[2] < tile_size or lq.shape[3] < tile_size):
+        tiled = False
+    if not tiled:
+        if min(lq.shape[2:]) < 512:
+            lq = resize_short_edge(lq, 512)
+        h0, w0 = lq.shape[2:]
+        return cleaner(pad_to_multiple(lq, 64))[:, :, :h0, :w0]
+    out = make_tiled_image_fn(cleaner, tile_size, tile_stride)(lq)
+    if min(out.shape[2:]) < 512:
+        out = resize_short_edge(out, 512)
+    return out
+
+
 # ------------------------------------------------------------------ colour fix / pipeline glue
 def wavelet_blur(img, radius: int):
     """3x3 binomial, dilation = radius, replicate pad — utils/common.py:29-47."""
@@ -254,19 +285,17 @@ def swinir_pipeline_run(lq_u8: np.ndarray, cleaner: Callable, encode_img: Callab
                         pos_prompt: str, neg_prompt: str, cfg_scale: float, sampler: str = "spaced",
                         cldm_tiled: bool = False, cldm_tile_size: int = 512,
                         cldm_tile_stride: int = 256, rescale_cfg: bool = False,
+                        cleaner_tiled: bool = False, cleaner_tile_size: int = 512, cleaner_tile_stride: int = 256,
                         x_T: Optional[torch.Tensor] = None,
                         noises: Optional[List[torch.Tensor]] = None, device="cpu",
                         set_strength: Optional[Callable] = None, taps: Optional[dict] = None):
-    """SwinIRPipeline.run (start_point 'noise', noise_aug 0, un-tiled cleaner / VAE) —
+    """SwinIRPipeline.run (start_point 'noise', noise_aug 0, un-tiled VAE) —
     pipeline.py:235-321, 71-233, 371-397.  Callables stand for the networks:
     cleaner(img01)->img01, encode_img(img_pm1)->latent, encode_txt(list)->c_txt,
     decode(latent)->img_pm1, model(x,t,cond)->eps."""
     lq = torch.tensor(lq_u8, dtype=torch.float32, device=device).div(255).clamp(0, 1).permute(0, 3, 1, 2).contiguous()
     out_size = tuple(lq.shape[2:])
-    if min(lq.shape[2:]) < 512:
-        lq = resize_short_edge(lq, 512)
-    h0, w0 = lq.shape[2:]
-    clean = cleaner(pad_to_multiple(lq, 64))[:, :, :h0, :w0]
+    clean = apply_cleaner(cleaner, lq, cleaner_tiled, cleaner_tile_size, cleaner_tile_stride)
     bs = clean.shape[0]
     cond_img = pad_to_multiple(clean, 8 if cldm_tiled else 64)
     cond = dict(c_txt=encode_txt([pos_prompt] * bs), c_img=encode_img(cond_img * 2 - 1))

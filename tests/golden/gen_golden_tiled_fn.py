@@ -1,0 +1,58 @@
+"""Golden fixture for the image-tiling wrapper and the tiled stage-1 branch, produced by the REFERENCE
+(`diffbir.utils.common.make_tiled_fn`, `SwinIRPipeline.apply_cleaner(tiled=True)`, imported read-only
+from /root/reference) with an analytic stand-in for the cleaner network.
+
+    python tests/golden/gen_golden_tiled_fn.py        ->  tests/golden/tiled_fn.npz
+"""
+import sys
+import typing
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle" / "_shims"))
+sys.path.insert(0, "/root/reference")
+torch.Tuple = typing.Tuple
+
+OUT = Path(__file__).resolve().parent
+
+
+def stand_in(t: torch.Tensor) -> torch.Tensor:
+    """Depends on the tile's content as a whole (mean), so the tiling is visible in the result."""
+    return torch.tanh(t) * 0.5 + t.mean(dim=(2, 3), keepdim=True) * 0.25
+
+
+@torch.no_grad()
+def main():
+    import diffbir.pipeline as P
+    from diffbir.utils.common import make_tiled_fn
+
+    class Null:
+        def __init__(self, *a, **k): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+    P.VRAMPeakMonitor = Null
+    g = torch.Generator().manual_seed(60)
+    x = torch.rand(2, 3, 72, 56, generator=g)
+    out = {"x": x.numpy(), "tiled_32_16": make_tiled_fn(stand_in, size=32, stride=16, progress=False)(x).numpy(),
+           "tiled_40_24": make_tiled_fn(stand_in, size=40, stride=24, progress=False)(x).numpy()}
+    lq = torch.rand(1, 3, 160, 136, generator=g)
+    pipe = P.SwinIRPipeline(stand_in, None, None, None, "cpu")
+    out["lq"] = lq.numpy()
+    # tiled, then resized to short edge 512; and an input smaller than a tile (un-tiled branch). The
+    # fixtures keep every 8th pixel (bit-exact comparison on the subsample keeps the file small).
+    full = pipe.apply_cleaner(lq, True, 128, 64)
+    tiny = pipe.apply_cleaner(lq[..., :100, :90], True, 128, 64)
+    out["cleaner_tiled_128_64_shape"] = np.array(full.shape)
+    out["cleaner_tiled_128_64_sub8"] = full[..., ::8, ::8].numpy()
+    out["cleaner_tiny_untiled_shape"] = np.array(tiny.shape)
+    out["cleaner_tiny_untiled_sub8"] = tiny[..., ::8, ::8].numpy()
+    np.savez_compressed(OUT / "tiled_fn.npz", **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,8 @@ def _oracle_run(pipe, lq, small, seed=231, **kw):
             cfg_scale=kw["cfg_scale"], sampler=kw["sampler_type"], cldm_tiled=kw["cldm_tiled"],
             rescale_cfg=kw["rescale_cfg"],
             cldm_tile_size=kw["cldm_tile_size"], cldm_tile_stride=kw["cldm_tile_stride"], device=dev,
+            cleaner_tiled=kw["cleaner_tiled"], cleaner_tile_size=kw["cleaner_tile_size"],
+            cleaner_tile_stride=kw["cleaner_tile_stride"],
             set_strength=lambda s: scales.update(s=[s] * 13), taps=taps)
     return out, taps
 
@@ -62,19 +64,20 @@ def _pipe(small, v_prediction=False):
     return pipe
 
 
-@pytest.mark.parametrize("sampler,steps,tiled", [("spaced", 10, False), ("ddim", 10, False), ("spaced", 4, True)])
-def test_small_pipeline_matches_oracle(sampler, steps, tiled):
+@pytest.mark.parametrize("sampler,steps,tiled,cleaner_tiled", [("spaced", 10, False, False), ("ddim", 10, False, False),
+                                                                ("spaced", 4, True, False), ("spaced", 4, True, True)])
+def test_small_pipeline_matches_oracle(sampler, steps, tiled, cleaner_tiled):
     pipe = _pipe(True)
     size = 640 if tiled else 512
     lq = synthetic_lq(size, size, seed=1)
-    kw = dict(RUN_DEFAULTS, steps=steps, sampler_type=sampler, cldm_tiled=tiled)
+    kw = dict(RUN_DEFAULTS, steps=steps, sampler_type=sampler, cldm_tiled=tiled, cleaner_tiled=cleaner_tiled)
     torch.manual_seed(231)
     out = pipe.run(lq, **kw)
     ref, taps = _oracle_run(pipe, lq, True, **kw)
     zp, zr = pipe.taps["z"], taps["z"]
     e = ((zp - zr).pow(2).mean().sqrt() / zr.pow(2).mean().sqrt()).item()
     p = _psnr_u8(out, ref)
-    print(f"small {sampler} x{steps} tiled={tiled}: latent rel-rms {e:.2e}, uint8 PSNR {p:.1f} dB, "
+    print(f"small {sampler} x{steps} tiled={tiled} cleaner_tiled={cleaner_tiled}: latent rel-rms {e:.2e}, uint8 PSNR {p:.1f} dB, "
           f"differing pixels {(out != ref).mean() * 100:.1f}%")
     assert out.shape == ref.shape == lq.shape and out.dtype == np.uint8
     assert e < 2e-2 and p > 45.0

@@ -104,3 +104,31 @@ def test_tiling_and_colour_fix(golden_dir):
     a, b = torch.from_numpy(g["wavelet_a"]), torch.from_numpy(g["wavelet_b"])
     np.testing.assert_allclose(osm.wavelet_reconstruction(a, b).numpy(), g["wavelet_out"], atol=1e-6)
     np.testing.assert_array_equal(osm.resize_short_edge(a, 64).numpy(), g["resize_out"])
+
+
+def test_tiled_image_fn_and_tiled_cleaner_match_reference():
+    """Image tiling wrapper + the tiled stage-1 branch: oracle AND product host code against the
+    fixture produced by the reference (tests/golden/gen_golden_tiled_fn.py), bit-exact on CPU."""
+    from oracle import sampling as osm
+    from diffbir_b200.pipeline import SwinIRPipeline
+    from diffbir_b200.utils.common import make_tiled_fn
+    from pathlib import Path
+    import pytest
+    g = np.load(Path(__file__).resolve().parent / "golden" / "tiled_fn.npz")
+
+    def stand_in(t):
+        return torch.tanh(t) * 0.5 + t.mean(dim=(2, 3), keepdim=True) * 0.25
+
+    x = torch.tensor(g["x"])
+    for size, stride in ((32, 16), (40, 24)):
+        ref = g[f"tiled_{size}_{stride}"]
+        np.testing.assert_array_equal(osm.make_tiled_image_fn(stand_in, size, stride)(x).numpy(), ref)
+        np.testing.assert_array_equal(make_tiled_fn(stand_in, size, stride)(x).numpy(), ref)
+    lq = torch.tensor(g["lq"])
+    pipe = SwinIRPipeline(stand_in, None, None, None, "cpu")
+    for name, inp in (("cleaner_tiled_128_64", lq), ("cleaner_tiny_untiled", lq[..., :100, :90])):
+        for out in (osm.apply_cleaner(stand_in, inp, True, 128, 64), pipe.apply_cleaner(inp, True, 128, 64)):
+            assert tuple(out.shape) == tuple(g[name + "_shape"])
+            np.testing.assert_array_equal(out[..., ::8, ::8].numpy(), g[name + "_sub8"])
+    with pytest.raises(ValueError):
+        pipe.apply_cleaner(torch.zeros(1, 3, 256, 256), True, 100, 50)
