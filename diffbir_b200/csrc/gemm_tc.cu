@@ -750,7 +750,8 @@ TilePlan pick_plan(const PlanQuery& q) {
 // factors change the fp32 summation order, so results can differ at rounding level between
 // processes; DBIR_GEMM_AUTOTUNE=0 keeps the deterministic model choice.
 using PlanKey = std::array<long long, 20>;
-std::mutex g_plan_mu;
+std::mutex g_plan_mu;                     // guards the cache
+std::mutex g_tune_mu;                     // serialises tuning (shared scratch / events, meaningful timings)
 std::map<PlanKey, TilePlan> g_plan_cache;
 int g_tuned_problems = 0;
 
@@ -853,6 +854,12 @@ TilePlan choose_plan(const dbir_gemm_args* a, cudaStream_t st, const PlanQuery& 
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return plan; }
   if (cs != cudaStreamCaptureStatusNone) return plan;       // cannot time inside a capture: model plan, not cached
+  std::lock_guard<std::mutex> tune_lk(g_tune_mu);
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);          // another thread may have tuned it meanwhile
+    auto it = g_plan_cache.find(key);
+    if (it != g_plan_cache.end()) return it->second;
+  }
   TilePlan tuned = plan;
   if (tune_plan(a, st, q, &tuned)) plan = tuned;
   std::lock_guard<std::mutex> lk(g_plan_mu);
