@@ -692,6 +692,9 @@ void for_each_plan(const PlanQuery& q, F f) {
   static const int pair_env = [] { const char* e = getenv("DBIR_GEMM_PAIR"); return e ? atoi(e) : -1; }();
   const int pair_mode = q.pair_req == 1 ? 1 : q.pair_req == 2 ? 0 : pair_env;
   const bool can_pair = pair_mode != 0 && !(q.m_tiles & 1);
+  // experiment switch (off: wide tiles only when they divide N): SS-mode MMAs run at 75-80 % of peak
+  // only for N = 256, so a ragged last tile can still pay for N = 640 / 1920
+  static const int ragged_wide = [] { const char* e = getenv("DBIR_GEMM_RAGGED_WIDE"); return e ? atoi(e) : 0; }();
   for (int i = 0; i < 10; ++i) {
     const int bn = cands[i % 5];
     const int pair = 1 - i / 5;
@@ -700,7 +703,7 @@ void for_each_plan(const PlanQuery& q, F f) {
     if (q.forced_bn > 0 && bn != q.forced_bn) continue;
     if (q.forced_bn <= 0) {
       if (q.geglu && bn < 64) continue;
-      if (bn > 64 && q.N % bn != 0) continue;          // ragged N only with the narrow tiles
+      if (bn > 64 && q.N % bn != 0 && !(ragged_wide && q.N > bn)) continue;   // ragged N only with the narrow tiles
     }
     const long long tiles = static_cast<long long>(q.m_tiles) * ((q.N + bn - 1) / bn);
     for (int s = 1; s <= 16; ++s) {
