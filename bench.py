@@ -182,9 +182,7 @@ def kernel_census(pipe, torch, lib):
     eng.two_streams = two
     fam, shapes = {}, {}
     names = {"gemm": "gemm+conv (gemm_tc_kernel)", "conv": "gemm+conv (gemm_tc_kernel)",
-             "attention": "attention (attn_fwd_kernel)", "gn_apply": "groupnorm apply (gn_apply_kernel)",
-             "gn_finalize": "groupnorm finalize (gn_finalize_kernel)", "gn_stats": "groupnorm stats (gn_stats_kernel)",
-             "layernorm": "layernorm (layernorm_kernel)"}
+             "attention": "attention (attn_fwd_kernel)"}
 
     def replay_ms(sel, reps=5):
         for c in sel:
@@ -306,11 +304,7 @@ def run_ours(args):
     gname = "gemm+conv (gemm_tc_kernel)"
     gf, gms, gn = fam[gname]
     achieved = gf / (gms * 1e-3) / 1e12
-    tensor_fams = (gname, "attention (attn_fwd_kernel)")
-    forward_ms = sum(v[1] for k, v in fam.items() if k in tensor_fams)
-    # bandwidth-bound families of the same forward: algorithmic bytes / in-graph time
-    norm = {k: {"ms_per_forward": v[1], "launches": v[2], "achieved_gb_s": v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0}
-            for k, v in fam.items() if k not in tensor_fams}
+    forward_ms = sum(v[1] for v in fam.values())
     traffic = None
     tpath = ROOT / "profiles" / "r01_ncu_full_summary.json"
     if tpath.exists():       # dram bytes (read + write) per launch from the committed `ncu --set full` capture
@@ -326,15 +320,13 @@ def run_ours(args):
             "attention": {"achieved": fam.get("attention (attn_fwd_kernel)", [0, 1, 0])[0] /
                           (fam.get("attention (attn_fwd_kernel)", [0, 1, 0])[1] * 1e-3) / 1e12,
                           "ms_per_forward": fam.get("attention (attn_fwd_kernel)", [0, 0, 0])[1]},
-            "tensor_kernel_ms_per_forward": forward_ms, "hbm_bound_families": norm}
+            "tensor_kernel_ms_per_forward": forward_ms}
     prof_dir = ROOT / "gpurun_out"
     prof_dir.mkdir(exist_ok=True)
     with open(prof_dir / "kernel_census.csv", "w") as f:
-        f.write("kind,shape,launches,gflop_or_gbyte,ms,tflops_or_gb_per_s\n")
+        f.write("kind,shape,launches,gflop,ms,tflops\n")
         for k, (fl, ms, n) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
-            tensor = k[0] in ("gemm", "conv", "attention")        # FLOP and TFLOP/s, else bytes and GB/s
-            rate = (fl / (ms * 1e-3) / (1e12 if tensor else 1e9)) if ms > 0 else 0.0
-            f.write(f"{k[0]},{'x'.join(map(str, k[1:]))},{n},{fl / 1e9:.2f},{ms:.4f},{rate:.1f}\n")
+            f.write(f"{k[0]},{'x'.join(map(str, k[1:]))},{n},{fl / 1e9:.2f},{ms:.4f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f}\n")
     # ---- CPU baseline (bounded sample) on the host cores, N = 1 only ------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -237,47 +237,31 @@ def gemm_gn_slots(conv_h=0, conv_w=0, rows_per_img=0) -> int:
     return int(load().dbir_gemm_gn_slots(conv_h, conv_w, rows_per_img))
 
 
-def _rec(kind, info, work, call):
-    """Runs `call`; while record_begin() is active also keeps it for in-graph replay (bench census).
-    `work` = FLOP for tensor-core kernels, algorithmic bytes for the bandwidth-bound ones."""
-    call()
-    if _record is not None:
-        _record.append((kind, info, work, call))
+def gn_finalize(p1, slots1, c1, p2, slots2, c2, n, hw, eps, stats):
+    check(load().dbir_gn_finalize(_fp(p1), slots1, c1, _fp(p2), slots2, c2, n, hw, C.c_float(eps), _fp(stats),
+                                  _sp()), "dbir_gn_finalize")
     count_launch()
 
 
-def gn_finalize(p1, slots1, c1, p2, slots2, c2, n, hw, eps, stats):
-    def call():
-        check(load().dbir_gn_finalize(_fp(p1), slots1, c1, _fp(p2), slots2, c2, n, hw, C.c_float(eps), _fp(stats),
-                                      _sp()), "dbir_gn_finalize")
-    _rec("gn_finalize", (n, hw, c1 + c2), 8.0 * n * (slots1 * c1 + slots2 * c2), call)
-
-
 def gn_stats(src1, src2, c1, c2, n, hw, eps, stats, workspace):
-    def call():
-        check(load().dbir_gn_stats(_fp(src1), _fp(src2), c1, c2, n, hw, C.c_float(eps), _fp(stats),
-                                   _fp(workspace), _sp()), "dbir_gn_stats")
-    _rec("gn_stats", (n, hw, c1 + c2), 4.0 * n * hw * (c1 + c2), call)
+    check(load().dbir_gn_stats(_fp(src1), _fp(src2), c1, c2, n, hw, C.c_float(eps), _fp(stats),
+                               _fp(workspace), _sp()), "dbir_gn_stats")
+    count_launch()
 
 
 def gn_apply(src1, src2, c1, c2, n, h, w, stats, gamma, beta, out, *, norm=True, silu=True,
              upsample=1, out_raw=None):
-    def call():
-        check(load().dbir_gn_apply(_fp(src1), _fp(src2), c1, c2, n, h, w, _fp(stats), _fp(gamma),
-                                   _fp(beta), 1 if norm else 0, 1 if silu else 0, upsample, _fp(out),
-                                   _fp(out_raw), _sp()), "dbir_gn_apply")
-    # fp32 read + 16-bit write(s)
-    _rec("gn_apply", (n, h * w, c1 + c2, upsample), n * h * w * (c1 + c2) * (4.0 + 2.0 * upsample * upsample +
-                                                                          (2.0 if out_raw is not None else 0.0)), call)
+    check(load().dbir_gn_apply(_fp(src1), _fp(src2), c1, c2, n, h, w, _fp(stats), _fp(gamma),
+                               _fp(beta), 1 if norm else 0, 1 if silu else 0, upsample, _fp(out),
+                               _fp(out_raw), _sp()), "dbir_gn_apply")
+    count_launch()
 
 
 def layernorm(x, ldx, rows, c, gamma, beta, out, ldo, eps=1e-5):
-    f32 = out.dtype == torch.float32
-
-    def call():
-        check(load().dbir_layernorm(_fp(x), C.c_int64(ldx), rows, c, _fp(gamma), _fp(beta),
-                                    C.c_float(eps), _fp(out), C.c_int64(ldo), 0 if f32 else 1, _sp()), "dbir_layernorm")
-    _rec("layernorm", (rows, c), rows * c * (8.0 if f32 else 6.0), call)
+    check(load().dbir_layernorm(_fp(x), C.c_int64(ldx), rows, c, _fp(gamma), _fp(beta),
+                                C.c_float(eps), _fp(out), C.c_int64(ldo),
+                                0 if out.dtype == torch.float32 else 1, _sp()), "dbir_layernorm")
+    count_launch()
 
 
 def swin_window_attention(qkv, ldq, batch, h, w, shift, bias_table, out, ldo):
