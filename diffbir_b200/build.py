@@ -1,6 +1,9 @@
 """In-tree build of libdiffbir_b200.so (sm_100a only; nvcc cross-compiles without a GPU).
 
-    python -m diffbir_b200.build [--bf16] [--force]
+    python -m diffbir_b200.build [--bf16] [--force] [-DNAME ...]
+
+Extra -D switches (also from $DBIR_BUILD_DEFS) select compile-time experiments, e.g.
+-DDBIR_GEMM_EARLY_B (weight tiles requested before griddepcontrol.wait) or -DDBIR_ATTN_PROBE.
 
 Objects go to diffbir_b200/csrc/_build/, the library to diffbir_b200/libdiffbir_b200.so
 (git-ignored; it travels to the GPU box with the gpurun snapshot).
@@ -32,10 +35,10 @@ def _digest(paths, extra):
     return h.hexdigest()
 
 
-def build_library(bf16: bool = False, force: bool = False, verbose: bool = False) -> Path:
+def build_library(bf16: bool = False, force: bool = False, verbose: bool = False, extra_defs=()) -> Path:
     srcs = sorted(CSRC.glob("*.cu"))
     hdrs = sorted(CSRC.glob("*.cuh")) + sorted((HERE.parent / "include").glob("*.h"))
-    defs = ["-DDBIR_OPERAND_BF16"] if bf16 else []
+    defs = (["-DDBIR_OPERAND_BF16"] if bf16 else []) + list(extra_defs) + os.environ.get("DBIR_BUILD_DEFS", "").split()
     bdir = CSRC / "_build"
     bdir.mkdir(exist_ok=True)
     stamp = bdir / "stamp.txt"
@@ -74,5 +77,5 @@ def build_library(bf16: bool = False, force: bool = False, verbose: bool = False
 
 if __name__ == "__main__":
     p = build_library(bf16="--bf16" in sys.argv, force="--force" in sys.argv,
-                      verbose="-v" in sys.argv)
+                      verbose="-v" in sys.argv, extra_defs=[a for a in sys.argv[1:] if a.startswith("-D")])
     print(p)
