@@ -132,3 +132,19 @@ def test_tiled_image_fn_and_tiled_cleaner_match_reference():
             np.testing.assert_array_equal(out[..., ::8, ::8].numpy(), g[name + "_sub8"])
     with pytest.raises(ValueError):
         pipe.apply_cleaner(torch.zeros(1, 3, 256, 256), True, 100, 50)
+
+
+def test_clip_text_tower_matches_reference(golden_dir):
+    """OpenCLIP text tower (penultimate layer, causal mask): the oracle's restatement AND the product's
+    TextTower (plain torch, run here on CPU) against the reference's FrozenOpenCLIPEmbedder output."""
+    from diffbir_b200.model.clip import TextTower
+    from tests.small_cfg import CLIP_SMALL
+    g = np.load(golden_dir / "clip_small.npz")
+    sd = make_state_dict(arch.clip_text_shapes(CLIP_SMALL), 7)
+    tokens = torch.tensor(g["tokens"])
+    ref = torch.tensor(g["out"])
+    with torch.no_grad():
+        o = ocl.clip_text_encode(sd, tokens, heads=CLIP_SMALL["heads"])
+        p = TextTower(sd, heads=CLIP_SMALL["heads"], layer="penultimate", device="cpu")(tokens)
+    assert (o - ref).abs().max() < 2e-5 * ref.abs().max()
+    assert (p - ref).abs().max() < 2e-5 * ref.abs().max()
