@@ -148,3 +148,14 @@ def test_clip_text_tower_matches_reference(golden_dir):
         p = TextTower(sd, heads=CLIP_SMALL["heads"], layer="penultimate", device="cpu")(tokens)
     assert (o - ref).abs().max() < 2e-5 * ref.abs().max()
     assert (p - ref).abs().max() < 2e-5 * ref.abs().max()
+
+
+def test_q_sample_matches_reference(golden_dir):
+    """Diffusion.q_sample (start point "cond", noise augmentation): oracle and product, bit-exact."""
+    from diffbir_b200.model import Diffusion
+    g = np.load(golden_dir / "qsample.npz")
+    x0, noise, t = torch.tensor(g["x0"]), torch.tensor(g["noise"]), torch.tensor(g["t"])
+    for name, kw in (("eps", {}), ("v", dict(parameterization="v", zero_snr=True))):
+        d = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000, **kw)
+        np.testing.assert_array_equal(d.q_sample(x0, t, noise).numpy(), g[f"q_{name}"])
+        np.testing.assert_array_equal(osm.q_sample(osm.make_betas(zero_snr=bool(kw)), x0, t, noise).numpy(), g[f"q_{name}"])
