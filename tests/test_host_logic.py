@@ -161,3 +161,26 @@ def test_gemm_planner_invariants():
     assert plan(64, 2560, 5, geglu=1, fbn=128)[:2] == (128, 1)
     # long-K, single-tile-row layers (8x8 latents) are split over k
     assert plan(1, 1280, 180)[1] > 1
+
+
+def test_integration_doc_struct_matches_binding_and_header():
+    """The ctypes mirror of dbir_gemm_args in INTEGRATION.md, the one in diffbir_b200/lib.py and the
+    C struct in include/diffbir_b200.h list the same fields in the same order."""
+    import re
+    from pathlib import Path
+    from diffbir_b200 import lib
+    root = Path(__file__).resolve().parents[1]
+    doc = (root / "INTEGRATION.md").read_text()
+    block = doc[doc.index("class GemmArgs"):doc.index("def _ck")]
+    doc_fields = re.findall(r'\("(\w+)",\s*C\.', block)
+    lib_fields = [f[0] for f in lib.GemmArgs._fields_]
+    assert doc_fields == lib_fields
+    hdr = (root / "include" / "diffbir_b200.h").read_text()
+    body = hdr[hdr.index("typedef struct dbir_gemm_args {"):hdr.index("} dbir_gemm_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = []
+    for decl in body.split("{", 1)[1].split(";"):
+        names = re.findall(r"[\*\s,](\w+)\s*(?=,|$)", decl.strip())
+        if decl.strip():
+            c_fields += [n for n in names if n not in ("const", "void", "float", "int32_t", "int64_t")]
+    assert c_fields == lib_fields
