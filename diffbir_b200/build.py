@@ -6,7 +6,8 @@ Extra -D switches (also from $DBIR_BUILD_DEFS) select compile-time experiments, 
 -DDBIR_GEMM_EARLY_B (weight tiles requested before griddepcontrol.wait) or -DDBIR_ATTN_PROBE.
 
 Objects go to diffbir_b200/csrc/_build/, the library to diffbir_b200/libdiffbir_b200.so
-(git-ignored; it travels to the GPU box with the gpurun snapshot).
+(git-ignored; it travels to the GPU box with the gpurun snapshot). --bf16 builds the bf16-operand
+variant into csrc/_build_bf16/ and libdiffbir_b200_bf16.so (loaded when DBIR_OPERANDS=bf16).
 """
 from __future__ import annotations
 
@@ -20,6 +21,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libdiffbir_b200.so"
+OUT_BF16 = HERE / "libdiffbir_b200_bf16.so"      # -DDBIR_OPERAND_BF16 variant, selected with DBIR_OPERANDS=bf16
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
@@ -39,12 +41,13 @@ def build_library(bf16: bool = False, force: bool = False, verbose: bool = False
     srcs = sorted(CSRC.glob("*.cu"))
     hdrs = sorted(CSRC.glob("*.cuh")) + sorted((HERE.parent / "include").glob("*.h"))
     defs = (["-DDBIR_OPERAND_BF16"] if bf16 else []) + list(extra_defs) + os.environ.get("DBIR_BUILD_DEFS", "").split()
-    bdir = CSRC / "_build"
+    bdir = CSRC / ("_build_bf16" if bf16 else "_build")
     bdir.mkdir(exist_ok=True)
+    out = OUT_BF16 if bf16 else OUT
     stamp = bdir / "stamp.txt"
     dig = _digest(srcs + hdrs, ARCH + FLAGS + defs)
-    if OUT.exists() and stamp.exists() and stamp.read_text() == dig and not force:
-        return OUT
+    if out.exists() and stamp.exists() and stamp.read_text() == dig and not force:
+        return out
 
     hdig = _digest(hdrs, ARCH + FLAGS + defs)
 
@@ -67,12 +70,12 @@ def build_library(bf16: bool = False, force: bool = False, verbose: bool = False
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [NVCC, *ARCH, "-shared", "-o", str(OUT), *map(str, objs), "-lcudart"]
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(out), *map(str, objs), "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")
     stamp.write_text(dig)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

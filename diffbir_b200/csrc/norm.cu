@@ -313,15 +313,14 @@ extern "C" int64_t dbir_gn_workspace_floats(int32_t n, int32_t hw, int32_t c) {
 }
 
 static int gn_chunks(int n, int hw, int* pix_per_chunk) {
-  // 32 pixels per chunk (4 per warp, loaded together) unless that would leave the GPU under-filled
-  // or exceed the partial buffer; at least 8 pixels (one per warp) per chunk
-  const int target = 2 * dbir_sm_count();
-  int chunks = (target + n - 1) / n;
-  int ppc = (hw + chunks - 1) / chunks;
-  if (ppc < 32 && hw * static_cast<long long>(n) >= 32LL * dbir_sm_count()) ppc = 32;
-  if (ppc < 8) ppc = 8;
-  chunks = (hw + ppc - 1) / ppc;
-  if (chunks > 1024) { chunks = 1024; ppc = (hw + chunks - 1) / chunks; chunks = (hw + ppc - 1) / ppc; }
+  // The chunking is a function of the image size only (never of the batch): the fp32 partial sums
+  // and hence the statistics of an image have the same bits whatever batch it is normalised in.
+  // 32 pixels per chunk (4 per warp, loaded together) for images of >= 2048 pixels, 8 (one per warp)
+  // below; at most 1024 chunks per image (the partial buffer).
+  (void)n;
+  int ppc = hw >= 2048 ? 32 : 8;
+  int chunks = (hw + ppc - 1) / ppc;
+  if (chunks > 1024) { ppc = (hw + 1023) / 1024; chunks = (hw + ppc - 1) / ppc; }
   *pix_per_chunk = ppc;
   return chunks;
 }

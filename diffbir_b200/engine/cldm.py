@@ -21,6 +21,7 @@ What is hoisted out of the per-step path (constant across sampler steps):
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -148,6 +149,12 @@ class CldmEngine:
         self._wseq, self._wpos = {}, {}  # per-stream weight sequence of the forward (L2 prefetch lookahead)
         self.prefetch_weights = False    # measured: no gain on B200 (7.53 vs 7.45 ms per forward), kept opt-in
         self.fuse_gn_stats = True
+        # Batch-invariant kernel plans: no split-K, whole attention tiles per CTA. Every sample's result
+        # then has the same bits whatever batch it runs in (tiled sampling: sharded == single rank) and
+        # whatever plan the timing-based tuner picked (run-to-run / process-to-process reproducible).
+        # DBIR_DETERMINISTIC=1 pins it for every forward; the samplers set it for tiled sampling.
+        self.deterministic = os.environ.get("DBIR_DETERMINISTIC", "0") == "1"
+        self.batch_invariant = self.deterministic
         self.emb_cur = None
         self._graphs = {}                # (shape, scales) -> (CUDAGraph, x_in, c_img, eps, launches)
         self.ws.on_grow = self._graphs.clear
@@ -234,6 +241,8 @@ class CldmEngine:
         pf = None
         if self.prefetch_weights and i + 1 < len(seq):
             pf = seq[i + 1]
+        if self.batch_invariant:
+            kw.setdefault("split_k", 1)
         lib.gemm(a, b, *args, splitk_ws=ws, prefetch=pf, **kw)
 
     def _emb(self, tag: str, l: arch.Layer, nb: int) -> torch.Tensor:
@@ -309,7 +318,7 @@ class CldmEngine:
         self._gemm(tag, a16, W[q + "qkv.w"], qkv, M=M, N=3 * c, K=c)
         att = ws.get(tag + ":at_o16", (M, c), self.op_dtype)
         nws = lib.attention_ws_bytes(nb, heads, hw, hw)
-        aws = ws.get(tag + ":at_sk", (nws // 4,), torch.float32, zero=True) if nws else None
+        aws = ws.get(tag + ":at_sk", (nws // 4,), torch.float32, zero=True) if nws and not self.batch_invariant else None
         lib.attention(qkv, qkv[:, c:], qkv[:, 2 * c:], att, batch=nb, heads=heads, sq=hw, skv=hw,
                       ldq=3 * c, ldk=3 * c, ldv=3 * c, ldo=c, ws=aws)
         self._gemm(tag, att, W[q + "o1.w"], t, M=M, N=c, K=c, bias=W[q + "o1.b"], residual=t)
@@ -383,7 +392,7 @@ class CldmEngine:
         """Returns (graph, x_in, c_img, eps, kernels_per_replay): static input/output buffers and
         a CUDA graph of forward(x_in, c_img) -> eps, captured once per (shape, strength) and
         reused across images (set_context / load_step only rewrite buffers the graph reads)."""
-        key = (nb, c, h, w, tuple(float(s) for s in control_scales), self.two_streams)
+        key = (nb, c, h, w, tuple(float(s) for s in control_scales), self.two_streams, self.batch_invariant)
         hit = self._graphs.get(key)
         if hit is not None:
             return hit

@@ -28,9 +28,49 @@ def load_config(name: str) -> dict:
         return yaml.safe_load(f)
 
 
+class _StubGlobal:
+    """Stands in for a pickled global that is not needed to read the tensors (Lightning callbacks,
+    hyper-parameter containers, ...)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        pass
+
+    def __call__(self, *a, **k):
+        return self
+
+
+class _TensorOnlyPickle:
+    """pickle_module for torch.load: resolves torch / numpy / stdlib container globals, stubs the rest.
+    Lightning-style SD checkpoints (v2-1_512-ema-pruned.ckpt, ...) carry non-tensor globals that
+    weights_only=True rejects; the reference uses a plain torch.load (utils/common.py:104-111)."""
+    import pickle as _pickle
+    __name__ = "diffbir_b200_tensor_only_pickle"
+    _SAFE = ("torch", "collections", "numpy", "builtins", "_codecs", "copyreg")
+
+    class Unpickler(_pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.split(".")[0] in _TensorOnlyPickle._SAFE and not (module == "builtins" and name in (
+                    "eval", "exec", "compile", "open", "__import__", "getattr", "setattr")):
+                return super().find_class(module, name)
+            return _StubGlobal
+
+    @staticmethod
+    def load(f, **kw):
+        return _TensorOnlyPickle.Unpickler(f, **kw).load()
+
+
 def load_checkpoint(path: str) -> dict:
-    """torch.load on CPU + the unwrapping of utils/common.py:104-120 (state_dict wrapper, module. prefix)."""
-    sd = torch.load(path, map_location="cpu", weights_only=True)
+    """torch.load on CPU + the unwrapping of utils/common.py:104-120 (state_dict wrapper, module. prefix).
+    Tries the safe tensors-only loader first; checkpoints with foreign pickled globals are re-read with
+    an unpickler that keeps the tensors and stubs everything else."""
+    import pickle
+    try:
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError:
+        sd = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_TensorOnlyPickle)
     if "state_dict" in sd:
         sd = sd["state_dict"]
     if sd and next(iter(sd)).startswith("module."):

@@ -10,8 +10,14 @@ from pathlib import Path
 
 import torch
 
+import os
+
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libdiffbir_b200.so"
+# DBIR_OPERANDS=bf16 loads the -DDBIR_OPERAND_BF16 build (bf16 tensor-core operands); default fp16 operands.
+_OPERANDS = os.environ.get("DBIR_OPERANDS", "fp16").lower()
+if _OPERANDS not in ("fp16", "bf16"):
+    raise ValueError(f"DBIR_OPERANDS={_OPERANDS!r}: expected fp16 or bf16")
+LIB_PATH = _HERE / ("libdiffbir_b200_bf16.so" if _OPERANDS == "bf16" else "libdiffbir_b200.so")
 _lib = None
 _launches = 0  # kernels launched through this binding (bench.py reports it)
 
@@ -49,7 +55,7 @@ def load():
         return _lib
     if not LIB_PATH.exists():
         raise DbirError(
-            f"{LIB_PATH} not found: build it with `python -m diffbir_b200.build` "
+            f"{LIB_PATH} not found: build it with `python -m diffbir_b200.build{' --bf16' if _OPERANDS == 'bf16' else ''}` "
             "(there is no CPU fallback)")
     lib = C.CDLL(str(LIB_PATH))
     lib.dbir_last_error.restype = C.c_char_p

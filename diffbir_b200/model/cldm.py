@@ -42,7 +42,7 @@ class ControlLDM:
         self.vae: Optional[VaeEngine] = None
         self.clip: Optional[TextTower] = None
         self._tokenizer = None
-        self._ctx_key = None
+        self._ctx_ref = None      # (tensor, version) the engine's cross-attention K/V were built from
         self._t_key = None
 
     # --------------------------------------------------------------- checkpoint loaders
@@ -84,7 +84,7 @@ class ControlLDM:
 
     def _invalidate(self):
         self.engine = self.vae = self.clip = None
-        self._ctx_key = self._t_key = None
+        self._ctx_ref = self._t_key = None
 
     def _build(self):
         if self.engine is None:
@@ -158,7 +158,7 @@ class ControlLDM:
     @torch.no_grad()
     def forward(self, x_noisy: torch.Tensor, t: torch.Tensor, cond: Dict[str, torch.Tensor]) -> torch.Tensor:
         """Generic entry (any sampler can call it): cldm.py:160-172. Context K/V and the time
-        embedding are cached on the identity of c_txt / the value of t."""
+        embedding are cached on the identity (+ in-place version) of c_txt / the value of t."""
         self._build()
         eng = self.engine
         nb = x_noisy.shape[0]
@@ -167,10 +167,12 @@ class ControlLDM:
         if nb > 1 and not bool((tv == tv[0]).all()):
             raise NotImplementedError("per-sample timesteps in one batch are not used by the samplers")
         c_txt = cond["c_txt"]
-        ck = (c_txt.data_ptr(), c_txt._version, tuple(c_txt.shape))
-        if ck != self._ctx_key:
+        # identity + version of a tensor we keep alive: a freed prompt's address can be handed to the
+        # next prompt by the caching allocator, so (data_ptr, shape) alone is not a safe key
+        ref = self._ctx_ref
+        if ref is None or ref[0] is not c_txt or ref[1] != c_txt._version:
             eng.set_context(c_txt.to(self.device, torch.float32))
-            self._ctx_key = ck
+            self._ctx_ref = (c_txt, c_txt._version)
         if (t0, nb) != self._t_key:
             eng.set_timesteps([t0], nb)
             eng.load_step(0)

@@ -12,7 +12,10 @@ When `model` is a diffbir_b200 ControlLDM the loop runs on the kernel engine:
     re-assembled by a single all-gather per step (every rank then blends and updates the same
     full latent with the same RNG stream).
 Noise is drawn with torch.randn_like once per step exactly like the reference
-(spaced_sampler.py:181, ddim_sampler.py:143), so seeds reproduce.
+(spaced_sampler.py:181, ddim_sampler.py:143): the RNG consumption is the reference's. Outputs are
+bit-reproducible across runs and processes in tiled mode and with DBIR_DETERMINISTIC=1 (batch-invariant
+kernel plans); otherwise the timing-based split-K choice of dbir_gemm may differ between processes
+(rounding-level differences).
 Any other callable `model(x, t, cond)` takes a plain PyTorch loop with identical arithmetic.
 """
 from __future__ import annotations
@@ -54,6 +57,27 @@ def assemble_gathered(recv: torch.Tensor) -> torch.Tensor:
     rest = recv.shape[3:]
     perm = (1, 2, 0) + tuple(range(3, recv.dim()))
     return recv.permute(*perm).reshape(nbr, slots * world, *rest).contiguous()
+
+
+def _sync_from_rank0(t: torch.Tensor, dev) -> torch.Tensor:
+    import torch.distributed as dist
+    t = t.to(dev).contiguous()
+    dist.broadcast(t, src=0)
+    return t
+
+
+def _sync_rng_from_rank0(dev) -> None:
+    """All ranks continue with rank 0's generator state (per-step randn_like must agree)."""
+    import torch.distributed as dist
+    dev = torch.device(dev)
+    if dev.type == "cuda":
+        st = torch.cuda.get_rng_state(dev).to(dev)
+        dist.broadcast(st, src=0)
+        torch.cuda.set_rng_state(st.cpu(), dev)
+    else:
+        st = torch.get_rng_state()
+        dist.broadcast(st, src=0)
+        torch.set_rng_state(st)
 
 
 class Sampler:
@@ -114,21 +138,29 @@ class Sampler:
         import torch.distributed as dist
         world, rank = ((dist.get_world_size(), dist.get_rank())
                        if (tiled and self.shard_tiles and dist.is_available() and dist.is_initialized()) else (1, 0))
+        if world > 1:
+            # Every rank must hold the same latent, condition and noise stream: rank 0's are authoritative
+            # (ranks seeded differently would otherwise blend tiles of diverging latents silently).
+            x = _sync_from_rank0(x, dev)
+            conds = [dict(cd, c_img=_sync_from_rank0(cd["c_img"].to(dev, torch.float32).contiguous(), dev))
+                     for cd in conds]
+            _sync_rng_from_rank0(dev)
 
         if tiled:
             wins = sliding_windows(H, W, tile_size, tile_stride)
             T = len(wins)
             all_coords = torch.tensor([[a, c] for a, _, c, _ in wins], dtype=torch.int32, device=dev)
-            mine = tiles_of_rank(T, rank, world)               # round-robin tile ownership
+            mine = tiles_of_rank(T, rank, world)               # round-robin tile ownership (may be empty: T < world)
             slots = tile_slots(T, world)
-            my_coords = all_coords[mine].contiguous()
             Tl, ts_ = len(mine), tile_size
+            my_coords = all_coords[mine].contiguous() if Tl else all_coords[:0]
             wts = torch.tensor(gaussian_weights(ts_, ts_), dtype=torch.float32, device=dev)
             nb = nbr * Tl * B
             c_img = torch.empty(nbr, Tl * B, C, ts_, ts_, device=dev)
             for j, cd in enumerate(conds):
-                lib.tile_gather(cd["c_img"].to(dev, torch.float32).contiguous(), B, C, H, W, my_coords,
-                                Tl, ts_, c_img[j])
+                if Tl:
+                    lib.tile_gather(cd["c_img"].to(dev, torch.float32).contiguous(), B, C, H, W, my_coords,
+                                    Tl, ts_, c_img[j])
             c_img = c_img.view(nb, C, ts_, ts_)
             ctx = torch.cat([cd["c_txt"].to(dev, torch.float32).repeat(Tl, 1, 1) for cd in conds], 0)
             gh = gw = ts_
@@ -141,12 +173,17 @@ class Sampler:
             ctx = torch.cat([cd["c_txt"].to(dev, torch.float32) for cd in conds], 0)
             gh, gw = H, W
         scales = [float(s) for s in model.control_scales]
-        eng.set_context(ctx)
-        eng.set_timesteps(model_ts, nb)
-        model._ctx_key = model._t_key = None                    # generic-path caches are now stale
-        eng.load_step(0)
-        graph, x_in, c_img_buf, eps, graph_launches = eng.graphed_forward(nb, C, gh, gw, scales)
-        c_img_buf.copy_(c_img)
+        # Tiled sampling pins the batch-invariant kernel plans (no split-K, whole attention tiles per
+        # CTA): a tile's eps then has the same bits whatever the per-rank batch is, so the sharded run
+        # is bit-identical to the single-rank run.
+        eng.batch_invariant = bool(tiled) or eng.deterministic
+        if nb > 0:
+            eng.set_context(ctx)
+            eng.set_timesteps(model_ts, nb)
+            model._ctx_ref = model._t_key = None                # generic-path caches are now stale
+            eng.load_step(0)
+            graph, x_in, c_img_buf, eps, graph_launches = eng.graphed_forward(nb, C, gh, gw, scales)
+            c_img_buf.copy_(c_img)
 
         def fill_inputs():
             if tiled:
@@ -160,19 +197,22 @@ class Sampler:
                     v[j].copy_(x)
 
         x_next = torch.empty_like(x)
+        self.last_stats = dict(world=world, tiles=(T if tiled else 0), tiles_this_rank=(Tl if tiled else 0),
+                               forwards_per_step=nb)
         for it, tab_idx in enumerate(order):
-            eng.load_step(it)
-            fill_inputs()
-            graph.replay()
-            lib.count_launch(graph_launches)
+            if nb > 0:
+                eng.load_step(it)
+                fill_inputs()
+                graph.replay()
+                lib.count_launch(graph_launches)
             if tiled:
-                ev = eps.view(nbr, Tl, B, C, ts_, ts_)
                 if world > 1:
-                    send[:, :Tl].copy_(ev)
+                    if Tl:
+                        send[:, :Tl].copy_(eps.view(nbr, Tl, B, C, ts_, ts_))
                     dist.all_gather_into_tensor(recv, send)
                     tiles = assemble_gathered(recv)             # global tile order, padding at the end
                 else:
-                    tiles = ev
+                    tiles = eps.view(nbr, Tl, B, C, ts_, ts_)
                 for j in range(nbr):
                     lib.tile_blend(tiles[j], B, C, H, W, all_coords, T, ts_, wts, eps_full[j])
                 e_c, e_u = eps_full[0], (eps_full[1] if use_cfg else None)
@@ -181,6 +221,8 @@ class Sampler:
                 e_c, e_u = ev[0], (ev[1] if use_cfg else None)
             noise = torch.randn_like(x)
             cur_cfg = self.get_cfg_scale(cfg_scale, model_ts[it])
+            if cur_cfg == 1.0:
+                e_u = None      # the reference takes the cond-only branch on such steps (spaced_sampler.py:150-152)
             lib.sampler_step(e_c, e_u, cur_cfg, x, noise, coefs[tab_idx], mode, x.numel(), x_next)
             x, x_next = x_next, x
         return x

@@ -119,3 +119,31 @@ def test_single_sample_file_name_and_configs(tmp_path):
     assert list(arch.unet_shapes(dict(cfg["controlnet_cfg"]), True)) == list(arch.unet_shapes(arch.CONTROLNET_CFG, True))
     sw = loop_mod.load_config("swinir.yaml")["params"]
     assert sw["embed_dim"] == arch.SWINIR_CFG["embed_dim"] and tuple(sw["depths"]) == arch.SWINIR_CFG["depths"]
+
+
+def test_load_checkpoint_with_foreign_pickled_globals(tmp_path):
+    """Lightning-style checkpoints carry non-tensor globals that weights_only=True rejects (ADVICE r1);
+    the loader falls back to an unpickler that keeps tensors and stubs everything else."""
+    import sys
+    import types
+
+    import torch
+
+    from diffbir_b200.inference.loop import load_checkpoint
+    mod = types.ModuleType("fake_lightning_callbacks")
+
+    class ModelCheckpoint:
+        def __init__(self):
+            self.best = 0.5
+
+    ModelCheckpoint.__module__, ModelCheckpoint.__qualname__ = "fake_lightning_callbacks", "ModelCheckpoint"
+    mod.ModelCheckpoint = ModelCheckpoint
+    sys.modules["fake_lightning_callbacks"] = mod
+    path = tmp_path / "lightning.ckpt"
+    try:
+        torch.save({"state_dict": {"module.w": torch.arange(6.0).view(2, 3)}, "callbacks": {"ckpt": ModelCheckpoint()},
+                    "epoch": 3}, path)
+    finally:
+        del sys.modules["fake_lightning_callbacks"]
+    sd = load_checkpoint(str(path))
+    assert list(sd) == ["w"] and torch.equal(sd["w"], torch.arange(6.0).view(2, 3))
