@@ -14,9 +14,18 @@ cond/uncond) -> VAE decode -> colour fix -> uint8.  Random-init SD-2.1 / SwinIR 
   cpu_baseline : the fp32 oracle port of the reference on the host cores, bounded sample
                  (1 of 50 sampler steps; SwinIR, VAE encode/decode once), extrapolated.
 
+  tiled2048 : EVERY line (N = 1, 2, 4, 8) also restores ONE 2048x2048 image with tiled sampling
+             (tile 512 / stride 256 -> 49 latent tiles, configs[3]): the tiles are sharded round-robin over
+             the ranks, one NCCL all-gather of the per-tile eps per step, every rank blends + updates
+             the full latent. Its MPix/s across N is the STRONG-scaling curve of the path that has a
+             collective; `value` stays the 512^2 replica throughput (weak scaling, no collective).
+  phases_ms : CUDA-event time of each pipeline stage of the 512^2 image
+  gpu_torch_baseline : the reference algorithm (oracle port) as stock PyTorch kernels on the same
+             GPU, fp16 autocast, bounded sample -- informational (SURVEY 8d "GPU baseline")
+
 Multi-GPU (torchrun, one rank per GPU): the 512x512 workload has no tiles, so ranks are
-independent replicas (weak scaling, no collective); --workload tiled2048 shards the 49 latent
-tiles of a 2048x2048 image over the ranks with one NCCL all-gather per step (strong scaling).
+independent replicas (weak scaling, no collective); --workload tiled2048 makes the tiled run the
+headline `value` instead (strong scaling).
 """
 import argparse
 import json
@@ -82,11 +91,22 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """(sustained bf16 TFLOP/s, burst bf16 TFLOP/s, HBM GB/s, source)"""
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return (d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0),
+                "measured (MEASURED_PEAKS.json)")
+    return 1400.0, 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads() -> int:
+    """Host threads the CPU arms use: every core this process may run on, whatever OMP_NUM_THREADS says
+    (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # ------------------------------------------------------------------------------------------
@@ -101,6 +121,7 @@ def cpu_reference_times(n_steps: int = 1, warm: int = 0, size: int = 512):
     from diffbir_b200.utils.synth import make_state_dict, synthetic_lq
     from oracle import cldm as ocl
     from oracle import swinir as osw
+    torch.set_num_threads(host_threads())
     torch.manual_seed(231)
     L = size // 8
     t = {}
@@ -152,7 +173,13 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BSR pipeline 512x512, 50-step spaced sampler, cfg 4.0, random-init SD2.1 UNet+ControlNet (configs[1])"},
-        "cpu_baseline": {"value": mpix, "unit": "MPix/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": mpix, "unit": "MPix/s", "cores": cores, "kind": "port", "sample": sample,
+                         "component_seconds": {"swinir": t["swinir"], "vae_encode": t["vae_encode"],
+                                               "vae_decode": t["vae_decode"], "sampler_step_median": step_s,
+                                               "sampler_steps": t["sampler_step"]},
+                         "note": ("CPU arm, independent of the GPU count: thread count forced to every host core "
+                                  "(torchrun's OMP_NUM_THREADS=1 is overridden); ratios against it are only "
+                                  "meaningful at N=1")},
         "e2e": {"value": mpix, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -167,6 +194,7 @@ def kernel_census(pipe, torch, lib):
     Returns per-family totals and the per-shape table (per-shape numbers from per-launch events)."""
     eng = pipe.cldm.engine
     dev = eng.dev
+    eng.batch_invariant = eng.deterministic      # the plans of the 512^2 loop (the tiled run pinned the invariant ones)
     x = torch.randn(2, 4, 64, 64, device=dev)
     ci = torch.randn(2, 4, 64, 64, device=dev) * 0.5
     eng.set_context(torch.randn(2, 77, 1024, device=dev))
@@ -214,10 +242,67 @@ def kernel_census(pipe, torch, lib):
     return fam, shapes
 
 
+def gpu_torch_baseline(torch, dev, n_steps: int = 3):
+    """Informational: the reference algorithm (oracle port = the reference's own op sequence) executed by
+    stock PyTorch kernels (cuDNN / cuBLAS / SDPA-free matmul attention) on this GPU under fp16 autocast,
+    on a bounded sample of the 512^2 workload; 50-step image time extrapolated. Not the product path."""
+    from diffbir_b200 import arch
+    from diffbir_b200.utils.synth import make_state_dict, synthetic_lq
+    from oracle import cldm as ocl
+    from oracle import swinir as osw
+
+    def todev(sd):
+        return {k: v.to(dev) for k, v in sd.items()}
+
+    def timed(fn, reps=1):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return r, e0.elapsed_time(e1) / reps
+
+    t = {}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ssd = todev(make_state_dict(arch.swinir_shapes(arch.SWINIR_CFG), 1238))
+        x = torch.tensor(synthetic_lq(512, 512)).float().div(255).permute(0, 3, 1, 2).contiguous().to(dev)
+        osw.swinir_forward(ssd, x)
+        clean, t["swinir"] = timed(lambda: osw.swinir_forward(ssd, x))
+        del ssd
+        vsd = todev(make_state_dict(arch.vae_shapes(arch.VAE_CFG), 1235))
+        ocl.vae_encode_mode(vsd, clean.float() * 2 - 1)
+        c_img, t["vae_encode"] = timed(lambda: ocl.vae_encode_mode(vsd, clean.float() * 2 - 1))
+        ocl.vae_decode(vsd, c_img / 0.18215)
+        _, t["vae_decode"] = timed(lambda: ocl.vae_decode(vsd, c_img / 0.18215))
+        del vsd
+        usd = todev(make_state_dict(arch.unet_shapes(arch.UNET_CFG), 1234, arch.is_zero_init))
+        csd = todev(make_state_dict(arch.unet_shapes(arch.CONTROLNET_CFG, True), 1237, arch.is_zero_init))
+        xt = torch.randn(1, 4, 64, 64, device=dev)
+        ctx = torch.randn(1, 77, 1024, device=dev)
+        tt = torch.full((1,), 999, device=dev)
+
+        def step():
+            ec = ocl.cldm_forward(usd, csd, xt, tt, ctx, c_img.float(), [1.0] * 13)
+            eu = ocl.cldm_forward(usd, csd, xt, tt, ctx, c_img.float(), [1.0] * 13)
+            return eu + 4.0 * (ec - eu)
+        step()
+        _, t["sampler_step"] = timed(step, n_steps)
+    total_ms = t["swinir"] + 2 * t["vae_encode"] + SAMPLER_STEPS * t["sampler_step"] + t["vae_decode"]
+    del usd, csd
+    torch.cuda.empty_cache()
+    return {"value": 512 * 512 / 1e6 / (total_ms / 1e3), "unit": "MPix/s", "ms_per_image": total_ms,
+            "component_ms": t, "kind": "oracle port of the reference on stock PyTorch CUDA kernels, fp16 autocast, eager",
+            "sample": f"SwinIR, VAE encode (x2 as the reference), decode once; {n_steps} sampler steps (2 forwards each) "
+                      "timed and extrapolated to 50"}
+
+
 def run_ours(args):
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     from diffbir_b200 import lib
+    from diffbir_b200.sampler import sampler as sampler_mod
     from diffbir_b200.utils.synth import RUN_DEFAULTS, build_synthetic_pipeline, synthetic_lq
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,17 +316,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     lib.load()
-    tiled = args.workload == "tiled2048"
-    size = 2048 if tiled else 512
-    kw = dict(RUN_DEFAULTS)
-    if tiled:
-        kw.update(cldm_tiled=True, cldm_tile_size=512, cldm_tile_stride=256)
+    headline_tiled = args.workload == "tiled2048"
     t_build = time.time()
     pipe = build_synthetic_pipeline(dev, seed=1234)
-    # replicas restore different images; the tiled workload restores ONE image on all ranks
-    lq = synthetic_lq(size, size, seed=0 if tiled else rank)
-    lq_pinned = torch.from_numpy(lq).pin_memory()
-    lq_dev = lq_pinned.to(dev)
     log(f"[rank {rank}] pipeline built in {time.time() - t_build:.1f}s")
 
     def barrier():
@@ -249,17 +326,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    # ------------------------------------------------------------------ 512^2 replicas
+    kw = dict(RUN_DEFAULTS)
+    lq = synthetic_lq(512, 512, seed=rank)            # replicas restore different images
+    lq_pinned = torch.from_numpy(lq).pin_memory()
+    lq_dev = lq_pinned.to(dev)
+
     def one(device_resident: bool):
         torch.manual_seed(231)
         if device_resident:
             return pipe.run_device(lq_dev, **kw)
         return pipe.run(lq_pinned, **kw)
 
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(args.warmup, 3)):              # W >= 3 (timing rules)
         one(True)
-    one(False)
+    out = one(False)
     barrier()
-
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -284,42 +372,104 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - w0) * 1e3
     barrier()
     clk = clocks.stop() if rank == 0 else None
+    # phase breakdown of one more image (CUDA events at the stage boundaries)
+    pipe.marks = []
+    one(True)
+    torch.cuda.synchronize()
+    phases = pipe.phases_ms()
+    pipe.marks = None
+    dev_ms, e2e_ms = reduce_max([dev_ms, e2e_ms])
+    mpix_512 = world * args.steps * 512 * 512 / 1e6
+    value_512, e2e_512 = mpix_512 / (dev_ms / 1e3), mpix_512 / (e2e_ms / 1e3)
 
-    times = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = times.tolist()
-    images = (1 if tiled else world) * args.steps
-    mpix_total = images * size * size / 1e6
-    value = mpix_total / (dev_ms / 1e3)
-    e2e = mpix_total / (e2e_ms / 1e3)
+    # ------------------------------------------------------------------ tiled 2048^2 (sharded, all-gather per step)
+    tiled = None
+    if not args.no_tiled:
+        tkw = dict(RUN_DEFAULTS, cldm_tiled=True, cldm_tile_size=512, cldm_tile_stride=256)
+        lq_t = synthetic_lq(2048, 2048, seed=0)       # ONE image, the same on all ranks
+        lq_t_pinned = torch.from_numpy(lq_t).pin_memory()
+        lq_t_dev = lq_t_pinned.to(dev)
+        torch.manual_seed(231)
+        pipe.run_device(lq_t_dev, **dict(tkw, steps=3))          # warm-up: plans, graph capture, NCCL channels
+        barrier()
+        sampler_mod.Sampler.time_collective = True
+        pipe.marks = []
+        t_ms, t_e2e_ms = [], []
+        for _ in range(args.tiled_images):
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.manual_seed(231)
+            a0.record()
+            pipe.run_device(lq_t_dev, **tkw)
+            a1.record()
+            barrier()
+            t_ms.append(a0.elapsed_time(a1))
+        tphases = pipe.phases_ms()
+        smp = pipe.last_sampler
+        ag = [a.elapsed_time(b) for a, b in smp.last_stats.get("allgather_events", [])]
+        stats = dict(smp.last_stats)
+        pipe.marks = None
+        sampler_mod.Sampler.time_collective = False
+        for _ in range(args.tiled_images):
+            barrier()
+            w0 = time.perf_counter()
+            torch.manual_seed(231)
+            out_t = pipe.run(lq_t_pinned, **tkw)
+            torch.cuda.synchronize()
+            t_e2e_ms.append((time.perf_counter() - w0) * 1e3)
+        barrier()
+        t_total, t_e2e_total, ag_mean, loop_ms, serial_ms = reduce_max(
+            [sum(t_ms), sum(t_e2e_ms), (sum(ag) / len(ag)) if ag else 0.0, tphases.get("sampler_loop", 0.0),
+             sum(v for k, v in tphases.items() if k != "sampler_loop")])
+        counts = torch.zeros(world, device=dev, dtype=torch.float64)
+        counts[rank] = stats.get("tiles_this_rank", 0)
+        if world > 1:
+            dist.all_reduce(counts)
+        mp = args.tiled_images * 2048 * 2048 / 1e6
+        tiled = {"value": mp / (t_total / 1e3), "unit": "MPix/s", "scaling": "strong", "images": args.tiled_images,
+                 "ms_per_image": t_total / args.tiled_images,
+                 "e2e": {"value": mp / (t_e2e_total / 1e3), "unit": "MPix/s", "h2d_bytes_per_step": int(lq_t.nbytes),
+                         "d2h_bytes_per_step": int(out_t.nbytes)},
+                 "tiles": int(stats.get("tiles", 0)), "tiles_per_rank": [int(c) for c in counts.tolist()],
+                 "tile_forwards_per_step_max_rank": int(2 * max(counts.tolist())),
+                 "allgather_ms_per_step": ag_mean, "allgather_bytes_per_rank_per_step":
+                     int(2 * ((stats.get("tiles", 0) + world - 1) // world) * 4 * 64 * 64 * 4) if world > 1 else 0,
+                 "sampler_loop_ms": loop_ms, "replicated_serial_ms": serial_ms,
+                 "phases_ms_rank0": tphases,
+                 "workload": "Tiled BSR 2048x2048, tile 512 stride 256: 49 latent tiles sharded round-robin over the ranks, "
+                             "one NCCL all-gather of per-tile eps per step (configs[3]); SwinIR / VAE / CLIP replicated"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel family (live CUDA events) --------------------------
-    peak_tf, _, peak_src = measured_peaks()
+    peak_tf, peak_burst, _, peak_src = measured_peaks()
     fam, shapes = kernel_census(pipe, torch, lib)
     gname = "gemm+conv (gemm_tc_kernel)"
     gf, gms, gn = fam[gname]
     achieved = gf / (gms * 1e-3) / 1e12
     forward_ms = sum(v[1] for v in fam.values())
     traffic = None
-    tpath = ROOT / "profiles" / "r01_ncu_full_summary.json"
-    if tpath.exists():       # dram bytes (read + write) per launch from the committed `ncu --set full` capture
-        rows = [r for r in json.loads(tpath.read_text()) if "gemm_tc_kernel" in r["kernel"]]
-        if rows:
-            traffic = {"dram_bytes_per_launch_mean": sum(r["dram_bytes"] for r in rows) / len(rows),
-                       "l2_to_sm_bytes_per_launch_mean": sum(r["l2_to_sm_bytes"] for r in rows) / len(rows),
-                       "launches": len(rows), "source": "profiles/r01_ncu_full_summary.json"}
+    for cand in ("r02_ncu_full_summary.json", "r01_ncu_full_summary.json"):
+        tpath = ROOT / "profiles" / cand
+        if tpath.exists():       # dram bytes (read + write) per launch from the committed `ncu --set full` capture
+            rows = [r for r in json.loads(tpath.read_text()) if "gemm_tc_kernel" in r["kernel"]]
+            if rows:
+                traffic = {"dram_bytes_per_launch_mean": sum(r["dram_bytes"] for r in rows) / len(rows),
+                           "l2_to_sm_bytes_per_launch_mean": sum(r["l2_to_sm_bytes"] for r in rows) / len(rows),
+                           "launches": len(rows), "source": f"profiles/{cand}"}
+                break
+    att = fam.get("attention (attn_fwd_kernel)", [0, 1, 0])
     roof = {"bound": "tensor", "kernel": gname, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
+            "frac": achieved / peak_tf, "frac_of_burst_peak": achieved / peak_burst, "peak_burst": peak_burst,
+            "peak_note": "frac = achieved / sustained cuBLAS bf16 peak (the family is timed inside a long step); "
+                         "frac_of_burst_peak uses the isolated-kernel figure",
+            "traffic": traffic, "peak_source": peak_src,
             "launches_per_forward": gn, "algorithmic_gflop_per_forward": gf / 1e9,
             "kernel_ms_per_forward": gms,
-            "attention": {"achieved": fam.get("attention (attn_fwd_kernel)", [0, 1, 0])[0] /
-                          (fam.get("attention (attn_fwd_kernel)", [0, 1, 0])[1] * 1e-3) / 1e12,
-                          "ms_per_forward": fam.get("attention (attn_fwd_kernel)", [0, 0, 0])[1]},
+            "attention": {"achieved": att[0] / (att[1] * 1e-3) / 1e12, "frac": att[0] / (att[1] * 1e-3) / 1e12 / peak_tf,
+                          "ms_per_forward": att[1]},
             "tensor_kernel_ms_per_forward": forward_ms}
     prof_dir = ROOT / "gpurun_out"
     prof_dir.mkdir(exist_ok=True)
@@ -327,9 +477,15 @@ def run_ours(args):
         f.write("kind,shape,launches,gflop,ms,tflops\n")
         for k, (fl, ms, n) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[0]},{'x'.join(map(str, k[1:]))},{n},{fl / 1e9:.2f},{ms:.4f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f}\n")
-    # ---- CPU baseline (bounded sample) on the host cores, N = 1 only ------------------------
-    cpu = None
+    # ---- baselines on the same box, N = 1 only ------------------------------------------------
+    cpu = gpu_base = None
     if world == 1 and not args.no_cpu_baseline:
+        del pipe
+        torch.cuda.empty_cache()
+        try:
+            gpu_base = gpu_torch_baseline(torch, dev)
+        except Exception as ex:                                   # informational only
+            gpu_base = {"unavailable": repr(ex)[:200]}
         t, cores = cpu_reference_times(n_steps=1)
         step_s = t["sampler_step"][0]
         total = cpu_image_seconds(t, step_s)
@@ -337,28 +493,35 @@ def run_ours(args):
                "sample": (f"oracle port, fp32: SwinIR {t['swinir']:.2f}s + VAE encode 2x{t['vae_encode']:.2f}s + "
                           f"1 of 50 sampler steps ({step_s:.2f}s, 2 forwards) x50 + VAE decode {t['vae_decode']:.2f}s "
                           f"= {total:.1f}s per 512^2 image (extrapolated)")}
+    wl_512 = "BSR pipeline 512x512, 50-step spaced sampler, cfg 4.0, random-init SD2.1 UNet+ControlNet (configs[1])"
     line = {
-        "metric": METRIC if not tiled else "MPix/s end-to-end 50-step restore, tiled 2048px",
-        "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if tiled else "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value_512, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate" if lib.operand_dtype() == torch.float16 else "bf16 operands / f32 accumulate",
         "data": "synthetic",
         "config": {
-            "workload": ("Tiled BSR 2048x2048, tile 512 stride 256 (49 latent tiles sharded over ranks, NCCL all-gather per step) (configs[3])"
-                         if tiled else
-                         "BSR pipeline 512x512, 50-step spaced sampler, cfg 4.0, random-init SD2.1 UNet+ControlNet (configs[1])"),
-            "images_per_gpu_per_step": 1, "sampler_steps": SAMPLER_STEPS,
-            "parallelism": "tiles sharded round-robin + all-gather" if tiled else "independent replicas, no collective",
+            "workload": wl_512, "images_per_gpu_per_step": 1, "sampler_steps": SAMPLER_STEPS,
+            "parallelism": "independent replicas, no collective (the sharded path with a collective is the tiled2048 block)",
             "l2": "no flush needed: each forward streams 2.6 GB of weights >> 126 MB L2",
         },
-        "e2e": {"value": e2e, "unit": "MPix/s", "h2d_bytes_per_step": int(lq.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+        "e2e": {"value": e2e_512, "unit": "MPix/s", "h2d_bytes_per_step": int(lq.nbytes), "d2h_bytes_per_step": int(out.nbytes),
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clk,
+        "phases_ms": phases,
+        "tiled2048": tiled,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "gpu_torch_baseline": gpu_base,
     }
+    if headline_tiled and tiled is not None:
+        line.update(metric="MPix/s end-to-end 50-step restore, tiled 2048px", value=tiled["value"],
+                    ms_per_step=tiled["ms_per_image"], scaling="strong", e2e=tiled["e2e"],
+                    steps=args.tiled_images)
+        line["config"]["workload"] = tiled["workload"]
+        line["config"]["parallelism"] = "tiles sharded round-robin + all-gather"
+        line["replicas512"] = {"value": value_512, "e2e": e2e_512, "ms_per_step": dev_ms / args.steps}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -371,7 +534,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="512", choices=["512", "tiled2048"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and GPU-torch baseline legs")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the tiled-2048 block")
+    ap.add_argument("--tiled-images", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -44,6 +44,21 @@ class Pipeline:
         self.device = device
         self.output_size: Tuple[int, int] = None
         self.taps: Optional[dict] = None   # set to {} to capture intermediates (tests)
+        self.marks: Optional[list] = None  # set to [] to record (phase, CUDA event) boundaries (bench.py phases_ms)
+
+    def _mark(self, name: str) -> None:
+        if self.marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def phases_ms(self) -> dict:
+        """Milliseconds between consecutive marks of the last run (call after a synchronize)."""
+        m = self.marks or []
+        out = {}
+        for (_, e0), (name, e1) in zip(m[:-1], m[1:]):
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
 
     def set_output_size(self, lq_size: Tuple[int]) -> None:
         h, w = lq_size[2:]
@@ -67,6 +82,7 @@ class Pipeline:
         # the latent is deterministic (posterior mode), so it is encoded once and shared.
         cond = self.cldm.prepare_condition(cond_img, [pos_prompt] * bs)
         uncond = dict(c_txt=self.cldm.clip(self.cldm.tokenize([neg_prompt] * bs)), c_img=cond["c_img"].clone())
+        self._mark("encode+clip")
         h1, w1 = cond["c_img"].shape[2:]
         if cldm_tiled and (h1 < cldm_tile_size // 8 or w1 < cldm_tile_size // 8):
             print("[Diffusion]: the input size is tiny and unnecessary to tile.")
@@ -103,8 +119,11 @@ class Pipeline:
                            cond=cond, uncond=uncond, cfg_scale=cfg_scale, tiled=cldm_tiled,
                            tile_size=cldm_tile_size // 8, tile_stride=cldm_tile_stride // 8, x_T=x_T,
                            progress=True)
+        self.last_sampler = sampler
+        self._mark("sampler_loop")
         z = z[..., :h1, :w1].contiguous()
         x = self.cldm.vae_decode(z)
+        self._mark("vae_decode")
         x = x[:, :, :h0, :w0]
         self.cldm.control_scales = control_scales
         if self.taps is not None:
@@ -137,9 +156,13 @@ class Pipeline:
                    neg_prompt, cfg_scale, start_point_type, sampler_type, noise_aug, rescale_cfg,
                    s_churn, s_tmin, s_tmax, s_noise, eta, order, x_T=None) -> torch.Tensor:
         """Same as run() with the uint8 NHWC input and output resident on the device."""
+        if self.marks is not None:
+            self.marks.clear()
+        self._mark("start")
         lq_tensor = lq_dev.to(torch.float32).div(255).clamp(0, 1).permute(0, 3, 1, 2).contiguous()
         self.set_output_size(lq_tensor.size())
         cond_img = self.apply_cleaner(lq_tensor, cleaner_tiled, cleaner_tile_size, cleaner_tile_stride)
+        self._mark("swinir")
         assert all(x >= 512 for x in cond_img.shape[2:]), (
             "The resolution of stage-1 model output should be greater than 512, "
             "since it will be used as condition for stage-2 model.")
@@ -152,7 +175,9 @@ class Pipeline:
                                  eta, order, x_T=x_T)
         sample = F.interpolate(wavelet_reconstruction((sample + 1) / 2, cond_img), size=self.output_size,
                                mode="bicubic", antialias=True)
-        return (sample * 255.0).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        out = (sample * 255.0).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        self._mark("post")
+        return out
 
 
 class SwinIRPipeline(Pipeline):

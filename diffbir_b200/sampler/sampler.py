@@ -81,6 +81,8 @@ def _sync_rng_from_rank0(dev) -> None:
 
 
 class Sampler:
+    time_collective = False        # record CUDA events around the per-step all-gather (bench.py sets it)
+
     def __init__(self, betas: np.ndarray, parameterization: str, rescale_cfg: bool):
         self.num_timesteps = len(betas)
         self.training_betas = betas
@@ -88,6 +90,7 @@ class Sampler:
         self.parameterization = parameterization
         self.rescale_cfg = rescale_cfg
         self.shard_tiles = True     # tiled sampling: shard tiles over torch.distributed ranks
+        self.last_stats: dict = {}
 
     def get_cfg_scale(self, default_cfg_scale: float, model_t: int) -> float:
         """Cosine CFG ramp — sampler/sampler.py:31-38."""
@@ -209,7 +212,13 @@ class Sampler:
                 if world > 1:
                     if Tl:
                         send[:, :Tl].copy_(eps.view(nbr, Tl, B, C, ts_, ts_))
+                    if self.time_collective:
+                        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ev0.record()
                     dist.all_gather_into_tensor(recv, send)
+                    if self.time_collective:
+                        ev1.record()
+                        self.last_stats.setdefault("allgather_events", []).append((ev0, ev1))
                     tiles = assemble_gathered(recv)             # global tile order, padding at the end
                 else:
                     tiles = eps.view(nbr, Tl, B, C, ts_, ts_)

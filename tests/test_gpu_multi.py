@@ -25,3 +25,33 @@ def test_sharded_tiles_bit_identical():
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "tiled_multi.log").write_text(r.stdout + "\n" + r.stderr)
     assert r.returncode == 0
+
+
+@pytest.mark.parametrize("small", [True, False])
+def test_batch_invariance_single_gpu(small):
+    """With the batch-invariant plans tiled sampling pins (no split-K, whole attention tiles), the eps of
+    a sample is bit-identical whatever batch it runs in -- the property that makes tiles sharded over R
+    ranks (per-rank batch 2*ceil(T/R)) bit-identical to the single-rank run."""
+    from diffbir_b200.utils.synth import build_synthetic_pipeline
+    pipe = build_synthetic_pipeline("cuda", 1234, small=small)
+    cl = pipe.cldm
+    cl._build()
+    eng = cl.engine
+    eng.batch_invariant = True
+    g = torch.Generator().manual_seed(3)
+    n_max = 7
+    L = 64 if small else 32
+    x = torch.randn(n_max, 4, L, L, generator=g).cuda()
+    ci = torch.randn(n_max, 4, L, L, generator=g).cuda()
+    ctx = torch.randn(n_max, 77, cl.unet_cfg["context_dim"], generator=g).cuda()
+
+    def run(n):
+        eng.set_context(ctx[:n].contiguous())
+        eng.set_timesteps([500], n)
+        eng.load_step(0)
+        return eng.forward(x[:n].contiguous(), ci[:n].contiguous(), [1.0] * 13).clone()
+
+    a, b, c = run(2), run(n_max), run(4)
+    assert torch.isfinite(a).all() and a.abs().max() > 0
+    assert torch.equal(a, b[:2]) and torch.equal(c, b[:4]), (
+        f"batch-dependent bits: max diff {(a - b[:2]).abs().max().item():.3e}")
