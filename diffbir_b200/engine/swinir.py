@@ -16,7 +16,7 @@ from typing import Dict
 import torch
 
 from .. import arch, lib
-from .common import Workspace, f32, op16, pack_conv3x3, pack_linear
+from .common import GraphCache, Workspace, f32, op16, pack_conv3x3, pack_linear
 
 
 def _pad_to(n: int, m: int) -> int:
@@ -41,6 +41,7 @@ class SwinIREngine:
         assert cfg["window_size"] == 8 and set(cfg["num_heads"]) == {6} and cfg["embed_dim"] == 180, \
             "window attention kernel is built for window 8, 6 heads x 30"
         self.ws = Workspace(self.dev)
+        self.graphs = GraphCache(self.ws)       # ~360 launches per image replayed as one graph per input shape
         self.op_dtype = lib.operand_dtype()
         c = cfg["embed_dim"]
         self.c, self.cp = c, _pad_to(c, 64)                     # 180 -> 192
@@ -92,8 +93,11 @@ class SwinIREngine:
         self.post_shift = torch.tensor(self.mean, dtype=torch.float32, device=dev)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x fp32 NCHW [nb, 3, H, W] in [0, 1], H and W multiples of 64 -> same shape."""
+        """x fp32 NCHW [nb, 3, H, W] in [0, 1], H and W multiples of 64 -> same shape (CUDA-graphed)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        return self.graphs.run(tuple(x.shape), self._forward, x)
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
         cfg, ws, W = self.cfg, self.ws, self.w
         nb, _, H, Wd = x.shape
         r = cfg["unshuffle_scale"]

@@ -16,7 +16,7 @@ from typing import Dict
 import torch
 
 from .. import arch, lib
-from .common import Workspace, f32, op16, pack_conv3x3, pack_linear
+from .common import GraphCache, Workspace, f32, op16, pack_conv3x3, pack_linear
 
 
 class VaeEngine:
@@ -30,8 +30,10 @@ class VaeEngine:
             if tuple(sd[k].shape) != tuple(shp):
                 raise ValueError(f"{k}: {tuple(sd[k].shape)} != {shp}")
         self.ws = Workspace(self.dev)
+        self.graphs = GraphCache(self.ws)       # decode / encode replayed as one graph per input shape
         self.op_dtype = lib.operand_dtype()
         self.w: Dict[str, torch.Tensor] = {}
+        self._part = {}                          # fp32 activation data_ptr -> (GN partial-sum buffer, slots)
         w, dev = self.w, self.dev
         for k, v in sd.items():
             if k not in shapes:
@@ -59,11 +61,28 @@ class VaeEngine:
 
     # ------------------------------------------------------------------ blocks
     def _gn(self, x, c, nb, h, w, gamma, beta, out16, silu, out_raw=None):
+        """GroupNorm(eps 1e-6)(+SiLU) -> 16-bit operand. Statistics come from the partial sums the
+        producing conv's epilogue emitted (dbir_gemm gn_partials -> dbir_gn_finalize: no second read of
+        the fp32 tensor); tensors written by other kernels take the stand-alone statistics pass."""
         ws = self.ws
         stats = ws.get("gn_stats", (nb * 64,), torch.float32)
-        wsp = ws.get("gn_ws", (lib.gn_workspace_floats(nb, h * w, c),), torch.float32, zero=True)
-        lib.gn_stats(x, None, c, 0, nb, h * w, 1e-6, stats, wsp)
+        part = self._part.get(x.data_ptr())
+        if part is not None:
+            lib.gn_finalize(part[0], part[1], c, None, 0, 0, nb, h * w, 1e-6, stats)
+        else:
+            wsp = ws.get("gn_ws", (lib.gn_workspace_floats(nb, h * w, c),), torch.float32, zero=True)
+            lib.gn_stats(x, None, c, 0, nb, h * w, 1e-6, stats, wsp)
         lib.gn_apply(x, None, c, 0, nb, h, w, stats, gamma, beta, out16, norm=True, silu=silu, out_raw=out_raw)
+
+    def _stats_kw(self, out: torch.Tensor, nb: int, n_cols: int, h: int, w: int) -> dict:
+        """kwargs that make a conv-mode dbir_gemm emit GroupNorm partial sums for its output `out`."""
+        slots = lib.gemm_gn_slots(h, w)
+        if slots <= 0:
+            self._part.pop(out.data_ptr(), None)
+            return {}
+        buf = self.ws.get(f"part:{out.data_ptr()}", (nb * slots * n_cols * 2,), torch.float32)
+        self._part[out.data_ptr()] = (buf, slots)
+        return dict(gn_partials=buf)
 
     def _res(self, p, x, cin, cout, nb, h, w, out):
         """ResnetBlock.forward (temb None) — vae.py:97-117."""
@@ -73,7 +92,7 @@ class VaeEngine:
         self._gn(x, cin, nb, h, w, W[p + "norm1.weight"], W[p + "norm1.bias"], a16, True, raw)
         h1 = ws.get("h1", (M, cout), torch.float32)
         lib.gemm(a16, W[p + "conv1.weight"], h1, M=M, N=cout, K=9 * cin, bias=W[p + "conv1.bias"],
-                 conv=(nb, h, w, cin, 3))
+                 conv=(nb, h, w, cin, 3), **self._stats_kw(h1, nb, cout, h, w))
         b16 = ws.get("b16", (M, cout), self.op_dtype)
         self._gn(h1, cout, nb, h, w, W[p + "norm2.weight"], W[p + "norm2.bias"], b16, True)
         if cin != cout:
@@ -83,7 +102,7 @@ class VaeEngine:
         else:
             res = x
         lib.gemm(b16, W[p + "conv2.weight"], out, M=M, N=cout, K=9 * cout, bias=W[p + "conv2.bias"],
-                 residual=res, conv=(nb, h, w, cout, 3))
+                 residual=res, conv=(nb, h, w, cout, 3), **self._stats_kw(out, nb, cout, h, w))
 
     def _attn(self, p, x, c, nb, h, w):
         """Single-head attention over pixels, in place on x — vae.py:232-282."""
@@ -109,12 +128,16 @@ class VaeEngine:
                 lib.softmax_rows(s, hw, r1 - r0, hw, float(c) ** -0.5, p16, hw)
                 lib.gemm(p16, vt, o16[b * hw + r0: b * hw + r1], M=r1 - r0, N=c, K=hw)
         lib.gemm(o16, W[p + "proj_out.weight"], x, M=M, N=c, K=c, bias=W[p + "proj_out.bias"], residual=x)
+        self._part.pop(x.data_ptr(), None)                       # x changed in place: its partials are stale
 
     # ------------------------------------------------------------------ decode
     def decode(self, z: torch.Tensor) -> torch.Tensor:
         """z fp32 NCHW [nb, 4, h, w] (already divided by the scale factor) -> image fp32 NCHW
         [nb, 3, 8h, 8w] in [-1, 1]."""
         assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous()
+        return self.graphs.run(("dec",) + tuple(z.shape), self._decode, z)
+
+    def _decode(self, z: torch.Tensor) -> torch.Tensor:
         cfg, ws, W = self.cfg, self.ws, self.w
         nb, zc, h, w = z.shape
         ch, mult, nres = cfg["ch"], tuple(cfg["ch_mult"]), cfg["num_res_blocks"]
@@ -129,6 +152,7 @@ class VaeEngine:
         c = ch * mult[-1]
         x = ws.get("x0", (nb * h * w, c), torch.float32)
         lib.conv3x3_small_cin(z2n, None, zc, 0, nb, h, w, W[p + "conv_in.weight"], W[p + "conv_in.bias"], c, x)
+        self._part.pop(x.data_ptr(), None)                       # written without GEMM partials
         self._res(p + "mid.block_1.", x, c, c, nb, h, w, x)
         self._attn(p + "mid.attn_1.", x, c, nb, h, w)
         self._res(p + "mid.block_2.", x, c, c, nb, h, w, x)
@@ -144,7 +168,8 @@ class VaeEngine:
                 lib.gn_apply(cur, None, c, 0, nb, h, w, None, None, None, up16, norm=False, silu=False, upsample=2)
                 o = ws.get(f"x{1 + flip}", (nb * 4 * h * w, c), torch.float32)
                 lib.gemm(up16, W[f"{p}up.{lvl}.upsample.conv.weight"], o, M=nb * 4 * h * w, N=c, K=9 * c,
-                         bias=W[f"{p}up.{lvl}.upsample.conv.bias"], conv=(nb, 2 * h, 2 * w, c, 3))
+                         bias=W[f"{p}up.{lvl}.upsample.conv.bias"], conv=(nb, 2 * h, 2 * w, c, 3),
+                         **self._stats_kw(o, nb, c, 2 * h, 2 * w))
                 cur, flip, h, w = o, flip ^ 1, 2 * h, 2 * w
         a16 = ws.get("a16", (nb * h * w, c), self.op_dtype)
         self._gn(cur, c, nb, h, w, W[p + "norm_out.weight"], W[p + "norm_out.bias"], a16, True)
@@ -157,6 +182,9 @@ class VaeEngine:
     def encode_moments(self, img: torch.Tensor) -> torch.Tensor:
         """img fp32 NCHW [nb, 3, H, W] in [-1, 1] -> moments fp32 NCHW [nb, 8, H/8, W/8]."""
         assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous()
+        return self.graphs.run(("enc",) + tuple(img.shape), self._encode_moments, img)
+
+    def _encode_moments(self, img: torch.Tensor) -> torch.Tensor:
         cfg, ws, W = self.cfg, self.ws, self.w
         nb, ic, h, w = img.shape
         ch, mult, nres = cfg["ch"], tuple(cfg["ch_mult"]), cfg["num_res_blocks"]
@@ -164,6 +192,7 @@ class VaeEngine:
         c = ch
         cur = ws.get("x0", (nb * h * w, c), torch.float32)
         lib.conv3x3_small_cin(img, None, ic, 0, nb, h, w, W[p + "conv_in.weight"], W[p + "conv_in.bias"], c, cur)
+        self._part.pop(cur.data_ptr(), None)                     # written without GEMM partials
         flip = 0
         for lvl in range(len(mult)):
             cout = ch * mult[lvl]
@@ -178,6 +207,7 @@ class VaeEngine:
                 o = ws.get(f"x{1 + flip}", (nb * ho * wo, c), torch.float32)
                 lib.gemm(col, W[f"{p}down.{lvl}.downsample.conv.weight"], o, M=nb * ho * wo, N=c, K=9 * c,
                          bias=W[f"{p}down.{lvl}.downsample.conv.bias"])
+                self._part.pop(o.data_ptr(), None)               # plain-mode GEMM: no partials requested
                 cur, flip, h, w = o, flip ^ 1, ho, wo
         self._res(p + "mid.block_1.", cur, c, c, nb, h, w, cur)
         self._attn(p + "mid.attn_1.", cur, c, nb, h, w)

@@ -154,6 +154,18 @@ class ControlLDM:
         return dict(c_txt=self.clip(self.tokenize(txt)),
                     c_img=self.vae_encode(cond_img * 2 - 1, sample=False, tiled=tiled, tile_size=tile_size))
 
+    @torch.no_grad()
+    def prepare_condition_pair(self, cond_img: torch.Tensor, pos_txt: List[str], neg_txt: List[str]):
+        """(cond, uncond) of Pipeline.apply_cldm (pipeline.py:116-128): the condition image is encoded
+        once (the posterior mode is deterministic, the reference encodes the same image twice) and both
+        prompt lists share one batched text-tower call."""
+        self._build()
+        n = len(pos_txt)
+        c_txt = self.clip(self.tokenize(list(pos_txt) + list(neg_txt)))
+        c_img = self.vae_encode(cond_img * 2 - 1, sample=False)
+        return (dict(c_txt=c_txt[:n].contiguous(), c_img=c_img),
+                dict(c_txt=c_txt[n:].contiguous(), c_img=c_img.clone()))
+
     # --------------------------------------------------------------- denoiser
     @torch.no_grad()
     def forward(self, x_noisy: torch.Tensor, t: torch.Tensor, cond: Dict[str, torch.Tensor]) -> torch.Tensor:

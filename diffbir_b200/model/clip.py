@@ -24,12 +24,35 @@ class TextTower:
         self.skip_last = 1 if layer == "penultimate" else 0
         self.n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.resblocks."))
         self.context_length = sd["positional_embedding"].shape[0]
+        self._graphs = {}            # token shape -> (CUDAGraph, static tokens, static output)
+        self.use_graphs = True
 
     @torch.no_grad()
     def __call__(self, tokens: torch.Tensor) -> torch.Tensor:
-        """tokens int64 [B, 77] -> fp32 [B, 77, width] (model/clip.py:37-59)."""
+        """tokens int64 [B, 77] -> fp32 [B, 77, width] (model/clip.py:37-59). On CUDA the ~280 small
+        library kernels of the tower are replayed as one CUDA graph per batch shape."""
+        tokens = tokens.to(self.dev)
+        if not (self.use_graphs and self.dev.type == "cuda") or torch.cuda.is_current_stream_capturing():
+            return self._forward(tokens)
+        key = tuple(tokens.shape)
+        hit = self._graphs.get(key)
+        if hit is None:
+            st = tokens.clone()
+            self._forward(st)                                   # warm-up (cuBLAS workspaces, SDPA selection)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward(st)
+            hit = (g, st, out)
+            self._graphs[key] = hit
+        g, st, out = hit
+        st.copy_(tokens)
+        g.replay()
+        return out.clone()
+
+    def _forward(self, tokens: torch.Tensor) -> torch.Tensor:
         sd = self.sd
-        x = sd["token_embedding.weight"][tokens.to(self.dev)] + sd["positional_embedding"]
+        x = sd["token_embedding.weight"][tokens] + sd["positional_embedding"]
         b, n, c = x.shape
         dh = c // self.heads
         for i in range(self.n_layers - self.skip_last):

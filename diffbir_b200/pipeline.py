@@ -80,8 +80,8 @@ class Pipeline:
         cond_img = pad_to_multiples_of(cond_img, multiple=8 if cldm_tiled else 64)
         # The reference encodes the (identical) condition image twice (pipeline.py:117-128);
         # the latent is deterministic (posterior mode), so it is encoded once and shared.
-        cond = self.cldm.prepare_condition(cond_img, [pos_prompt] * bs)
-        uncond = dict(c_txt=self.cldm.clip(self.cldm.tokenize([neg_prompt] * bs)), c_img=cond["c_img"].clone())
+        # Both prompts go through the text tower as one batch (pipeline.py:117-128 runs it twice).
+        cond, uncond = self.cldm.prepare_condition_pair(cond_img, [pos_prompt] * bs, [neg_prompt] * bs)
         self._mark("encode+clip")
         h1, w1 = cond["c_img"].shape[2:]
         if cldm_tiled and (h1 < cldm_tile_size // 8 or w1 < cldm_tile_size // 8):

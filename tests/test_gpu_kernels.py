@@ -395,3 +395,42 @@ def test_fused_groupnorm_statistics(L, n, h, w, c1, c2):
     st = stats.view(n, 32, 2)
     assert (st[..., 0].double() - mean).abs().max() < 1e-4 * (mean.abs().max() + 1)
     assert ((st[..., 1].double() - 1 / (var + 1e-5).sqrt()).abs() / (1 / (var + 1e-5).sqrt())).max() < 1e-4
+
+
+@pytest.mark.parametrize("b,h,w,shift", [(1, 64, 64, 0), (1, 64, 64, 4), (2, 16, 24, 4), (1, 128, 64, 4)])
+def test_swin_window_attention(L, b, h, w, shift):
+    """dbir_swin_window_attention stand-alone (WindowAttention.forward + roll / partition / reverse /
+    shift mask, swinir.py:120-151, 245-285) vs the oracle's op sequence in fp32 on the same 16-bit qkv."""
+    from oracle.swinir import rel_pos_index, shift_mask
+    heads, dh, ws = 6, 30, 8
+    c = heads * dh
+    g = torch.Generator().manual_seed(11)
+    lib, dt = L, L.operand_dtype()
+    ld = 544
+    qkv = torch.zeros(b * h * w, ld, dtype=dt, device="cuda")
+    qkv[:, :3 * c] = (torch.randn(b * h * w, 3 * c, generator=g) * 1.5).to("cuda", dt)
+    table = (torch.randn(225, heads, generator=g) * 0.5).cuda()
+    out = torch.zeros(b * h * w, 192, dtype=dt, device="cuda")
+    lib.swin_window_attention(qkv, ld, b, h, w, shift, table, out, 192)
+    # reference (fp32, on the fp16/bf16-rounded qkv)
+    y = qkv[:, :3 * c].float().view(b, h, w, 3 * c)
+    if shift:
+        y = torch.roll(y, (-shift, -shift), (1, 2))
+    win = y.view(b, h // ws, ws, w // ws, ws, 3 * c).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, 3 * c)
+    nwin = win.shape[0]
+    t = win.view(nwin, ws * ws, 3, heads, dh).permute(2, 0, 3, 1, 4)
+    q, k, v = t[0] * dh ** -0.5, t[1], t[2]
+    attn = q @ k.transpose(-1, -2)
+    bias = table[rel_pos_index(ws).to("cuda").view(-1)].view(ws * ws, ws * ws, heads).permute(2, 0, 1)
+    attn = attn + bias[None]
+    if shift:
+        m = shift_mask(h, w, ws, shift, "cuda")
+        attn = (attn.view(b, m.shape[0], heads, ws * ws, ws * ws) + m[None, :, None]).view(nwin, heads, ws * ws, ws * ws)
+    o = (torch.softmax(attn, dim=-1) @ v).transpose(1, 2).reshape(nwin, ws * ws, c)
+    o = o.view(b, h // ws, w // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h, w, c)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    ref = o.reshape(b * h * w, c)
+    err = rel_err(out[:, :c], ref)
+    assert err < (4e-3 if dt == torch.float16 else 2e-2), err
+    assert out[:, c:].abs().max().item() == 0.0      # pad columns untouched
