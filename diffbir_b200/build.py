@@ -37,13 +37,15 @@ def _digest(paths, extra):
     return h.hexdigest()
 
 
-def build_library(bf16: bool = False, force: bool = False, verbose: bool = False, extra_defs=()) -> Path:
+def build_library(bf16: bool = False, force: bool = False, verbose: bool = False, extra_defs=(), tag: str = "") -> Path:
+    """tag: experiment builds (extra -D switches) go to libdiffbir_b200_<tag>.so / csrc/_build_<tag>/ and
+    are loaded with DBIR_LIB_TAG=<tag>; the product libraries are the untagged fp16 / bf16 ones."""
     srcs = sorted(CSRC.glob("*.cu"))
     hdrs = sorted(CSRC.glob("*.cuh")) + sorted((HERE.parent / "include").glob("*.h"))
     defs = (["-DDBIR_OPERAND_BF16"] if bf16 else []) + list(extra_defs) + os.environ.get("DBIR_BUILD_DEFS", "").split()
-    bdir = CSRC / ("_build_bf16" if bf16 else "_build")
+    bdir = CSRC / (f"_build_{tag}" if tag else "_build_bf16" if bf16 else "_build")
     bdir.mkdir(exist_ok=True)
-    out = OUT_BF16 if bf16 else OUT
+    out = HERE / f"libdiffbir_b200_{tag}.so" if tag else OUT_BF16 if bf16 else OUT
     stamp = bdir / "stamp.txt"
     dig = _digest(srcs + hdrs, ARCH + FLAGS + defs)
     if out.exists() and stamp.exists() and stamp.read_text() == dig and not force:
@@ -79,6 +81,8 @@ def build_library(bf16: bool = False, force: bool = False, verbose: bool = False
 
 
 if __name__ == "__main__":
+    tags = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--tag=")]
     p = build_library(bf16="--bf16" in sys.argv, force="--force" in sys.argv,
-                      verbose="-v" in sys.argv, extra_defs=[a for a in sys.argv[1:] if a.startswith("-D")])
+                      verbose="-v" in sys.argv, extra_defs=[a for a in sys.argv[1:] if a.startswith("-D")],
+                      tag=tags[0] if tags else "")
     print(p)

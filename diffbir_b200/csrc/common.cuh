@@ -430,8 +430,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// GELU(x) = x * Phi(x) with the exact-erf definition (F.gelu default; attention.py:19-45, swinir.py:27).
+// erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, below fp32 erff's own ulp for the 16-bit
+// outputs these epilogues feed): branch-free, one MUFU.RCP + one MUFU.EX2 + 9 FMA-pipe ops, where
+// libdevice's erff costs ~30 instructions and a divergent branch per element -- the GEGLU / MLP
+// epilogues (K = C, so the mainloop is only 5-20 k-blocks long) were bound by it.
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx(-1.4426950408889634f * z * z);
+  const float half_erfc = 0.5f * p * e;                 // 0.5 * erfc(|x| / sqrt 2)
+  // Phi(x) = 1 - half_erfc for x >= 0, half_erfc for x < 0
+  const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  return x * phi;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

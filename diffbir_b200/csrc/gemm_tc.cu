@@ -55,6 +55,8 @@ struct GemmParams {
   float act_param;
   int geglu;               // 1: tile holds [BN/2 values | BN/2 gates]; output width N/2
   int bias_per_row;        // bias indexed by output row instead of column
+  // grouped launch: G same-shape problems back to back along M; group g's weights / bias start at row g*N
+  int group_span;          // m-tiles (plain) or images (conv) per group; 0 = one problem
   // split-K: grid.z CTAs share one output tile; partial tiles go through `ws`, the last CTA to
   // arrive (ticket) sums them in fixed order (deterministic) and runs the epilogue.
   int splits, kb_per_split;
@@ -108,6 +110,7 @@ struct EpiCtx {
   int row0;                // plain mode: first global row of this warp
   int x, y, n;             // conv mode: origin of this warp's sub-box
   long long stats_base;    // element offset of this warp's (image, slot) row in the stats buffer, < 0: none
+  int grp_off;             // grouped launch: row offset of this CTA's problem in the stacked bias
   __device__ __forceinline__ uint32_t out_buf(int b) const { return epi_base + b * EPI_TILE_BYTES; }
   __device__ __forceinline__ uint32_t res_buf(int b) const { return epi_base + (2 + b) * EPI_TILE_BYTES; }
   __device__ __forceinline__ uint32_t bar(int b) const { return res_bar + b * 8; }
@@ -176,12 +179,12 @@ __device__ __forceinline__ void finish_chunk(const GemmParams& p, EpiCtx& e, flo
       } else if (ncols == 32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + gc0 + j));
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + e.grp_off + gc0 + j));
           v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gc0 + j);
+        for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + e.grp_off + gc0 + j);
       }
     }
     if (p.rowvec && out_row >= 0) {
@@ -312,6 +315,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     x0 = tx * p.bw; y0 = ty * p.bh; n0 = t * p.bni;
   }
 
+  // grouped launch: this CTA's problem -> row offset into the stacked weights / bias
+  int grp_off = 0;
+  if (p.group_span > 0) grp_off = ((p.mode == 1 ? n0 : m_tile) / p.group_span) * p.N;
+
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -344,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0) {
     if (elect_one()) {
       const uint32_t fbar_e = PAIR ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
-      const int b_row_e = n_tile * BN + static_cast<int>(cta_rank) * B_ROWS;
+      const int b_row_e = grp_off + n_tile * BN + static_cast<int>(cta_rank) * B_ROWS;
       for (int it = 0; it < early_iters; ++it) {
         if (cta_rank == 0) mbar_expect_tx(&full[it], (PAIR ? 2 : 1) * (A_STAGE_BYTES + B_STAGE_BYTES));
 #pragma unroll
@@ -367,7 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0) {
     // ---------------- TMA producer: warp-uniform loop, one elected lane issues -------------
     const uint32_t fbar0 = PAIR ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
-    const int b_row = n_tile * BN + static_cast<int>(cta_rank) * B_ROWS;
+    const int b_row = grp_off + n_tile * BN + static_cast<int>(cta_rank) * B_ROWS;
     // conv mode: (channel block, tap column, tap row) of the next k-block, advanced incrementally
     // (integer divisions in this loop cost more than the TMA issue itself)
     int cb = 0, tx = 0, ty = 0;
@@ -479,6 +486,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int vec_idx = 0;
     EpiCtx e;
     e.tm_out = &tma_out; e.tm_res = &tma_res;
+    e.grp_off = grp_off;
     e.res_bar = smem_u32(res_bars + ew * 2);
     e.row0 = m_tile * BM + q * 32;
     e.x = e.y = e.n = 0;
@@ -536,11 +544,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int col = n_tile * BN + c_first + i * CSTEP + lane;
           float x = 0.f;
           if (c_first + i * CSTEP < BN && col < p.N) {
-            if (p.bias) x = __ldg(p.bias + col);
+            if (p.bias) x = __ldg(p.bias + grp_off + col);
             if (p.rowvec && any_row) x += __ldg(p.rowvec + static_cast<long long>(vsel) * p.N + col);
           }
           pre[i] = x;
         }
+      }
+    }
+    // GEGLU: value / gate biases of every chunk this warp finishes (lane == column), fetched while the
+    // mainloop runs and broadcast with shuffles (the per-element __ldg pair this replaces sat on the
+    // epilogue's critical path)
+    constexpr int MAX_G = (BN / 2) / CSTEP + 1;
+    float pa[MAX_G], pg[MAX_G];
+    if (p.geglu) {
+#pragma unroll
+      for (int i = 0; i < MAX_G; ++i) {
+        const int c = c_first + i * CSTEP + lane;
+        const bool live = p.bias && c_first + i * CSTEP < BN / 2 && n_tile * (BN / 2) + c < p.N / 2;
+        pa[i] = live ? __ldg(p.bias + grp_off + n_tile * BN + c) : 0.f;
+        pg[i] = live ? __ldg(p.bias + grp_off + n_tile * BN + BN / 2 + c) : 0.f;
       }
     }
     mbar_wait(tmem_full, 0);
@@ -634,8 +656,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int n_half = p.N / 2;
       if constexpr (HB % 32 == 0) {
         int ci = 0;
-#pragma unroll 1
-        for (int c0 = c_first; c0 < HB; c0 += CSTEP) {
+#pragma unroll
+        for (int i = 0; i < MAX_G; ++i) {
+          const int c0 = c_first + i * CSTEP;
+          if (c0 >= HB) break;
           uint32_t av[32], ag[32];
           __syncwarp();
           tmem_ld32(taddr + c0, av);
@@ -647,12 +671,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(av[j]);
-            float g = __uint_as_float(ag[j]);
-            if (p.bias && j < ncols) {
-              a += __ldg(p.bias + n_tile * BN + c0 + j);
-              g += __ldg(p.bias + n_tile * BN + HB + c0 + j);
-            }
+            const float a = __uint_as_float(av[j]) + __shfl_sync(0xffffffffu, pa[i], j);
+            const float g = __uint_as_float(ag[j]) + __shfl_sync(0xffffffffu, pg[i], j);
             v[j] = a * gelu_erf_f(g);
           }
           finish_chunk(p, e, v, lane, ci, gc0, ncols, -1, out_row, vec_idx, false);
@@ -803,7 +823,7 @@ PlanKey make_key(const dbir_gemm_args* a) {
   k[i++] = a->out_kind; k[i++] = a->geglu; k[i++] = a->force_bn; k[i++] = a->split_k; k[i++] = a->cta_pair;
   k[i++] = a->residual != nullptr; k[i++] = a->gn_partials != nullptr;
   k[i++] = a->splitk_ws ? a->splitk_ws_bytes : 0;
-  k[i++] = a->lda; k[i++] = a->ldo; k[i++] = a->act;
+  k[i++] = a->lda; k[i++] = a->ldo; k[i++] = a->act * 8 + (a->groups > 1 ? a->groups : 1);
   return k;
 }
 
@@ -946,6 +966,16 @@ int gemm_impl(const dbir_gemm_args* a, cudaStream_t st, const TilePlan* forced) 
   p.has_residual = a->residual != nullptr;
   p.alpha = a->alpha; p.act = a->act; p.act_param = a->act_param; p.geglu = a->geglu;
   p.bias_per_row = a->bias_per_row;
+  const int groups = a->groups > 1 ? a->groups : 1;
+  if (groups > 1) {
+    DBIR_REQUIRE(!a->bias_per_row, "dbir_gemm: groups and bias_per_row are exclusive");
+    DBIR_REQUIRE(a->N % 4 == 0, "dbir_gemm: grouped launches need N %% 4 == 0 (stacked bias alignment)");
+    if (a->a_mode == 0)
+      DBIR_REQUIRE(a->M % groups == 0 && (a->M / groups) % BM == 0,
+                   "dbir_gemm: grouped launch needs M/groups (= %d) to be a multiple of %d rows", a->M / groups, BM);
+    else
+      DBIR_REQUIRE(a->img_n % groups == 0, "dbir_gemm: grouped conv needs img_n %% groups == 0");
+  }
   p.dbg = reinterpret_cast<long long*>(a->debug_stamps);
   p.pf_ptr = reinterpret_cast<const char*>(a->prefetch_ptr);
   p.pf_bytes = a->prefetch_ptr ? a->prefetch_bytes : 0;
@@ -965,6 +995,7 @@ int gemm_impl(const dbir_gemm_args* a, cudaStream_t st, const TilePlan* forced) 
     if (dbir_make_tmap(&ta, a->a, 2, dims, strides, box, 2, 1)) return -3;
     p.num_kb = (a->K + BK - 1) / BK;
     m_tiles = (a->M + BM - 1) / BM;
+    if (groups > 1) p.group_span = (a->M / groups) / BM;
     // output / residual: 32 x 32 element boxes per epilogue warp
     uint64_t odims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(a->M)};
     uint64_t ostr[1] = {static_cast<uint64_t>(a->ldo) * eb};
@@ -1002,6 +1033,10 @@ int gemm_impl(const dbir_gemm_args* a, cudaStream_t st, const TilePlan* forced) 
     if (dbir_make_tmap(&ta, a->a, 4, dims, strides, box, 2, 1)) return -3;
     p.num_kb = taps * p.cblocks;
     m_tiles = p.tiles_x * p.tiles_y * ((NI + bni - 1) / bni);
+    if (groups > 1) {
+      DBIR_REQUIRE((NI / groups) % bni == 0, "dbir_gemm: grouped conv: a %d-image tile would straddle two groups", bni);
+      p.group_span = NI / groups;
+    }
     // per-warp sub-box of 32 pixels: (wbw x wbh x wbn)
     const int wbw = bw < 32 ? bw : 32;
     const int wbh = bh < 32 / wbw ? bh : 32 / wbw;
@@ -1037,7 +1072,11 @@ int gemm_impl(const dbir_gemm_args* a, cudaStream_t st, const TilePlan* forced) 
   }
   constexpr long long TICKET_FLOATS = 16384;
   const long long ws_floats = a->splitk_ws ? a->splitk_ws_bytes / 4 - TICKET_FLOATS : 0;
-  const PlanQuery pq{m_tiles, a->N, p.num_kb, a->geglu, a->force_bn, a->split_k, a->cta_pair, ws_floats};
+  // CTA pairs share one weight tile between two adjacent m-tiles: in a grouped launch a pair must not
+  // straddle two problems
+  int pair_req = a->cta_pair;
+  if (groups > 1 && ((m_tiles / groups) & 1)) pair_req = 2;
+  const PlanQuery pq{m_tiles, a->N, p.num_kb, a->geglu, a->force_bn, a->split_k, pair_req, ws_floats};
   const TilePlan plan = forced ? *forced : choose_plan(a, st, pq);
   const int bn = plan.bn;
   p.splits = plan.splits;
@@ -1048,7 +1087,7 @@ int gemm_impl(const dbir_gemm_args* a, cudaStream_t st, const TilePlan* forced) 
   }
   {
     const long long ldb = a->ldb > 0 ? a->ldb : a->K;
-    uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N)};
+    uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N) * groups};
     uint64_t strides[1] = {static_cast<uint64_t>(ldb) * 2};
     uint32_t box[2] = {BK, static_cast<uint32_t>(plan.pair ? bn / 2 : bn)};
     if (dbir_make_tmap(&tb, a->b, 2, dims, strides, box, 2, 1)) return -3;

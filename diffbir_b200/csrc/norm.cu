@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int c1, int c2,
                 int h, int w, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int do_norm, int do_silu, int up,
-                op_t* __restrict__ out, op_t* __restrict__ out_raw, int pix_per_cta) {
+                op_t* __restrict__ out, op_t* __restrict__ out_raw, int pix_per_cta, int imgs_per_group) {
   extern __shared__ float s_ab[];   // [C][2]
   pdl_trigger();
   pdl_wait();
@@ -197,12 +197,13 @@ gn_apply_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
   const int hw = h * w;
   if (do_norm) {
     const int cpg = C / 32;
+    const int goff = imgs_per_group > 0 ? (n / imgs_per_group) * C : 0;     // stacked twin problems
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g = c / cpg;
       const float mean = stats[(n * 32 + g) * 2], rstd = stats[(n * 32 + g) * 2 + 1];
-      const float a = gamma[c] * rstd;
+      const float a = gamma[goff + c] * rstd;
       s_ab[2 * c] = a;
-      s_ab[2 * c + 1] = beta[c] - mean * a;
+      s_ab[2 * c + 1] = beta[goff + c] - mean * a;
     }
     __syncthreads();
   }
@@ -249,12 +250,16 @@ template <bool F32OUT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, int rows, int C,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                 void* __restrict__ out_v, long long ldo) {
+                 void* __restrict__ out_v, long long ldo, int rows_per_group) {
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
+  if (rows_per_group > 0) {                      // stacked twin problems: this row's gamma / beta set
+    const long long goff = (row / rows_per_group) * C;
+    gamma += goff; beta += goff;
+  }
   const float* xr = x + row * ldx;
   constexpr int MAXV = 10;
   float4 v[MAXV];
@@ -356,7 +361,7 @@ extern "C" int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, i
                              int32_t n, int32_t h, int32_t w, const float* stats,
                              const float* gamma, const float* beta, int32_t do_norm,
                              int32_t do_silu, int32_t upsample, void* out, void* out_raw,
-                             void* stream) {
+                             int32_t imgs_per_group, void* stream) {
   const int C = c1 + c2;
   DBIR_REQUIRE(src1 && out, "dbir_gn_apply: null pointer");
   DBIR_REQUIRE(c1 % 4 == 0 && c2 % 4 == 0, "dbir_gn_apply: channels must be multiples of 4");
@@ -372,13 +377,13 @@ extern "C" int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, i
   const size_t smem = do_norm ? static_cast<size_t>(C) * 2 * sizeof(float) : 0;
   DBIR_CHECK_CUDA(dbir_launch(gn_apply_kernel, dim3(ctas, n), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream),
                               src1, src2, c1, c2, h, w, stats, gamma, beta, do_norm, do_silu, upsample,
-                              reinterpret_cast<op_t*>(out), reinterpret_cast<op_t*>(out_raw), ppc));
+                              reinterpret_cast<op_t*>(out), reinterpret_cast<op_t*>(out_raw), ppc, imgs_per_group));
   return 0;
 }
 
 extern "C" int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t c,
                               const float* gamma, const float* beta, float eps, void* out,
-                              int64_t ldo, int32_t out_kind, void* stream) {
+                              int64_t ldo, int32_t out_kind, int32_t rows_per_group, void* stream) {
   DBIR_REQUIRE(x && gamma && beta && out, "dbir_layernorm: null pointer");
   DBIR_REQUIRE(c % 4 == 0 && c <= 1280 && ldo >= c && ldo % 4 == 0 && ldo <= 1280,
                "dbir_layernorm: unsupported width %d (ldo %lld)", c, (long long)ldo);
@@ -387,9 +392,9 @@ extern "C" int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t
   const long long ldx_ = ldx, ldo_ = ldo;
   if (out_kind == 0)
     DBIR_CHECK_CUDA(dbir_launch(layernorm_kernel<true>, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
-                                x, ldx_, rows, c, gamma, beta, eps, out, ldo_));
+                                x, ldx_, rows, c, gamma, beta, eps, out, ldo_, rows_per_group));
   else
     DBIR_CHECK_CUDA(dbir_launch(layernorm_kernel<false>, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
-                                x, ldx_, rows, c, gamma, beta, eps, out, ldo_));
+                                x, ldx_, rows, c, gamma, beta, eps, out, ldo_, rows_per_group));
   return 0;
 }

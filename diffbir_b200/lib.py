@@ -18,6 +18,8 @@ _OPERANDS = os.environ.get("DBIR_OPERANDS", "fp16").lower()
 if _OPERANDS not in ("fp16", "bf16"):
     raise ValueError(f"DBIR_OPERANDS={_OPERANDS!r}: expected fp16 or bf16")
 LIB_PATH = _HERE / ("libdiffbir_b200_bf16.so" if _OPERANDS == "bf16" else "libdiffbir_b200.so")
+if os.environ.get("DBIR_LIB_TAG"):      # experiment builds: python -m diffbir_b200.build --tag=<tag> -D...
+    LIB_PATH = _HERE / f"libdiffbir_b200_{os.environ['DBIR_LIB_TAG']}.so"
 _lib = None
 _launches = 0  # kernels launched through this binding (bench.py reports it)
 
@@ -38,7 +40,7 @@ class GemmArgs(C.Structure):
         ("rows_per_vec", C.c_int32), ("out_kind", C.c_int32), ("act", C.c_int32),
         ("geglu", C.c_int32), ("force_bn", C.c_int32),
         ("alpha", C.c_float), ("act_param", C.c_float),
-        ("bias_per_row", C.c_int32), ("reserved0", C.c_int32),
+        ("bias_per_row", C.c_int32), ("groups", C.c_int32),
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
         ("split_k", C.c_int32), ("cta_pair", C.c_int32),
@@ -147,7 +149,7 @@ ACT = {None: 0, "none": 0, "gelu": 1, "lrelu": 2, "silu": 3}
 def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual=None,
          lda=0, ldb=0, ldo=None, ldr=None, conv=None, act=None, act_param=0.0, alpha=1.0,
          geglu=False, force_bn=0, bias_per_row=False, out2=None, ldo2=None, splitk_ws=None,
-         split_k=0, cta_pair=0, debug_stamps=None, gn_partials=None, gn_rows_per_img=0, prefetch=None):
+         split_k=0, cta_pair=0, debug_stamps=None, gn_partials=None, gn_rows_per_img=0, prefetch=None, groups=1):
     """out = residual + alpha * act(A @ B^T + bias + rowvec). conv = (n, h, w, c, ksize)."""
     lib = load()
     g = GemmArgs()
@@ -171,6 +173,7 @@ def gemm(a, b, out, *, M, N, K, bias=None, rowvec=None, rows_per_vec=0, residual
     g.geglu = 1 if geglu else 0
     g.force_bn = force_bn
     g.bias_per_row = 1 if bias_per_row else 0
+    g.groups = groups
     g.out2 = _ptr(out2)
     g.ldo2 = (n_out if ldo2 is None else ldo2)
     if splitk_ws is not None:
@@ -256,17 +259,17 @@ def gn_stats(src1, src2, c1, c2, n, hw, eps, stats, workspace):
 
 
 def gn_apply(src1, src2, c1, c2, n, h, w, stats, gamma, beta, out, *, norm=True, silu=True,
-             upsample=1, out_raw=None):
+             upsample=1, out_raw=None, imgs_per_group=0):
     check(load().dbir_gn_apply(_fp(src1), _fp(src2), c1, c2, n, h, w, _fp(stats), _fp(gamma),
                                _fp(beta), 1 if norm else 0, 1 if silu else 0, upsample, _fp(out),
-                               _fp(out_raw), _sp()), "dbir_gn_apply")
+                               _fp(out_raw), imgs_per_group, _sp()), "dbir_gn_apply")
     count_launch()
 
 
-def layernorm(x, ldx, rows, c, gamma, beta, out, ldo, eps=1e-5):
+def layernorm(x, ldx, rows, c, gamma, beta, out, ldo, eps=1e-5, rows_per_group=0):
     check(load().dbir_layernorm(_fp(x), C.c_int64(ldx), rows, c, _fp(gamma), _fp(beta),
                                 C.c_float(eps), _fp(out), C.c_int64(ldo),
-                                0 if out.dtype == torch.float32 else 1, _sp()), "dbir_layernorm")
+                                0 if out.dtype == torch.float32 else 1, rows_per_group, _sp()), "dbir_layernorm")
     count_launch()
 
 

@@ -54,7 +54,10 @@ typedef struct dbir_gemm_args {
   float alpha;          /* scale applied before the residual add (control strength) */
   float act_param;
   int32_t bias_per_row; /* 1: bias[row] instead of bias[col] (transposed products) */
-  int32_t reserved0;
+  int32_t groups;       /* 0/1 = one problem. G > 1: G same-shape problems in one launch (e.g. the UNet and
+                           ControlNet encoders' twin layers): A / out / residual / rowvec / gn_partials hold the G
+                           problems back to back along M (M = total rows, divisible by G; conv: img_n divisible by
+                           G), b is [G*N, ldb] and bias [G*N] (group g's weights at rows g*N). */
   void* out2;           /* optional op16 copy of the result [rows, ldo2] (operand of the next op) */
   int64_t ldo2;
   void* splitk_ws;      /* optional split-K scratch (zero-initialised once by the caller, >= 64 KiB +
@@ -126,10 +129,12 @@ int dbir_gn_stats(const float* src1, const float* src2, int32_t c1, int32_t c2, 
 int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, int32_t c2, int32_t n,
                   int32_t h, int32_t w, const float* stats, const float* gamma,
                   const float* beta, int32_t do_norm, int32_t do_silu, int32_t upsample,
-                  void* out, void* out_raw, void* stream);
+                  void* out, void* out_raw, int32_t imgs_per_group, void* stream);
 int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t c, const float* gamma,
                    const float* beta, float eps, void* out, int64_t ldo, int32_t out_kind,
-                   void* stream);   /* out_kind 0 = fp32, 1 = op16 */
+                   int32_t rows_per_group, void* stream);   /* out_kind 0 = fp32, 1 = op16 */
+/* imgs_per_group / rows_per_group > 0: stacked twin problems (see dbir_gemm_args.groups) -- image n /
+ * row r takes gamma / beta at offset (n / imgs_per_group) * C resp. (r / rows_per_group) * c. 0 = one set. */
 
 /* ---- SwinIR window attention -----------------------------------------------------------
  * One 8x8 window per CTA; qkv op16 [batch*h*w, ldq] with columns [q | k | v] x (heads, dim)

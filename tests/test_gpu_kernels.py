@@ -434,3 +434,84 @@ def test_swin_window_attention(L, b, h, w, shift):
     err = rel_err(out[:, :c], ref)
     assert err < (4e-3 if dt == torch.float16 else 2e-2), err
     assert out[:, c:].abs().max().item() == 0.0      # pad columns untouched
+
+
+@pytest.mark.parametrize("M,N,K,geglu", [(256, 320, 320, False), (1024, 640, 640, False), (256, 1280, 1280, False),
+                                         (512, 2560, 320, True)])
+def test_gemm_grouped_plain(L, M, N, K, geglu):
+    """groups = 2 (twin UNet / ControlNet layers stacked along M, weights / bias stacked along N) is
+    bit-identical to the two separate launches with the split pinned off (same per-row arithmetic)."""
+    from diffbir_b200.engine.common import pack_geglu
+    dt = L.operand_dtype()
+    G = 2
+    a = rnd(G * M, K, seed=1).to(dt)
+    ws = [rnd(N, K, seed=10 + g, scale=K ** -0.5) for g in range(G)]
+    bs = [rnd(N, seed=20 + g) for g in range(G)]
+    kw = dict(split_k=1)
+    if geglu:
+        packed = [pack_geglu(w, b, 128, "cuda") for w, b in zip(ws, bs)]
+        ws, bs = [p[0] for p in packed], [p[1] for p in packed]
+        kw.update(geglu=True, force_bn=128)
+        n_out, res = N // 2, None
+    else:
+        ws = [w.to(dt) for w in ws]
+        n_out, res = N, rnd(G * M, N, seed=4)
+    wcat, bcat = torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
+    out_dt = dt if geglu else torch.float32
+    out = torch.empty(G * M, n_out, device="cuda", dtype=out_dt)
+    L.gemm(a, wcat, out, M=G * M, N=N, K=K, bias=bcat, residual=res, groups=G, **kw)
+    for g in range(G):
+        sep = torch.empty(M, n_out, device="cuda", dtype=out_dt)
+        L.gemm(a[g * M:(g + 1) * M], ws[g], sep, M=M, N=N, K=K, bias=bs[g],
+               residual=None if res is None else res[g * M:(g + 1) * M], **kw)
+        assert torch.equal(out[g * M:(g + 1) * M], sep), f"group {g}"
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 64, 64, 320, 320), (2, 8, 8, 1280, 1280), (1, 16, 16, 640, 1280)])
+def test_gemm_grouped_conv(L, n, h, w, cin, cout):
+    dt = L.operand_dtype()
+    G = 2
+    x = rnd(G * n, h, w, cin, seed=1).to(dt)
+    wp = [rnd(cout, 9 * cin, seed=10 + g, scale=(9 * cin) ** -0.5).to(dt) for g in range(G)]
+    bs = [rnd(cout, seed=20 + g) for g in range(G)]
+    rv = rnd(G * n, cout, seed=4)
+    M = n * h * w
+    out = torch.empty(G * M, cout, device="cuda")
+    slots = L.gemm_gn_slots(h, w)
+    part = torch.zeros(G * n * slots * cout * 2, device="cuda")
+    L.gemm(x, torch.cat(wp, 0).contiguous(), out, M=G * M, N=cout, K=9 * cin, bias=torch.cat(bs, 0).contiguous(),
+           rowvec=rv, conv=(G * n, h, w, cin, 3), groups=G, split_k=1, gn_partials=part)
+    for g in range(G):
+        sep = torch.empty(M, cout, device="cuda")
+        psep = torch.zeros(n * slots * cout * 2, device="cuda")
+        L.gemm(x[g * n:(g + 1) * n], wp[g], sep, M=M, N=cout, K=9 * cin, bias=bs[g], rowvec=rv[g * n:(g + 1) * n],
+               conv=(n, h, w, cin, 3), split_k=1, gn_partials=psep)
+        assert torch.equal(out[g * M:(g + 1) * M], sep), f"group {g}"
+        assert torch.equal(part.view(G, -1)[g], psep), f"group {g} statistics"
+
+
+def test_norm_kernels_grouped(L):
+    """gn_apply / layernorm with stacked twin problems pick gamma / beta by image / row group."""
+    dt = L.operand_dtype()
+    n, h, w, c = 2, 16, 16, 320
+    x = rnd(2 * n, h, w, c, seed=1)
+    gam, bet = rnd(2 * c, seed=2), rnd(2 * c, seed=3)
+    stats = torch.empty(2 * n * 64, device="cuda")
+    wsp = torch.zeros(L.gn_workspace_floats(2 * n, h * w, c), device="cuda")
+    L.gn_stats(x, None, c, 0, 2 * n, h * w, 1e-5, stats, wsp)
+    out = torch.empty(2 * n * h * w, c, device="cuda", dtype=dt)
+    L.gn_apply(x, None, c, 0, 2 * n, h, w, stats, gam, bet, out, norm=True, silu=True, imgs_per_group=n)
+    for g in range(2):
+        sep = torch.empty(n * h * w, c, device="cuda", dtype=dt)
+        L.gn_apply(x[g * n:(g + 1) * n].contiguous(), None, c, 0, n, h, w, stats[g * n * 64:(g + 1) * n * 64].contiguous(),
+                   gam[g * c:(g + 1) * c].contiguous(), bet[g * c:(g + 1) * c].contiguous(), sep, norm=True, silu=True)
+        assert torch.equal(out[g * n * h * w:(g + 1) * n * h * w], sep)
+    rows = 512
+    t = rnd(2 * rows, c, seed=5)
+    o = torch.empty(2 * rows, c, device="cuda", dtype=dt)
+    L.layernorm(t, c, 2 * rows, c, gam, bet, o, c, rows_per_group=rows)
+    for g in range(2):
+        sep = torch.empty(rows, c, device="cuda", dtype=dt)
+        L.layernorm(t[g * rows:(g + 1) * rows], c, rows, c, gam[g * c:(g + 1) * c].contiguous(),
+                    bet[g * c:(g + 1) * c].contiguous(), sep, c)
+        assert torch.equal(o[g * rows:(g + 1) * rows], sep)
