@@ -358,3 +358,15 @@ def tile_blend(tiles, b, c, h, w, coords, ntiles, tile, weights, out):
     check(load().dbir_tile_blend(_fp(tiles), b, c, h, w, _fp(coords), ntiles, tile, _fp(weights),
                                  _fp(out), _sp()), "dbir_tile_blend")
     count_launch()
+
+
+def wavelet_fix(sample, style, out_u8=None, out_f32=None):
+    """Fused colour fix (+ uint8 quantisation): sample NCHW view in [-1, 1], style NCHW view in [0, 1],
+    both fp32 with unit column stride; exactly one of out_u8 (NHWC uint8) / out_f32 (NCHW fp32)."""
+    b, c, h, w = sample.shape
+    assert c == 3 and tuple(style.shape) == (b, c, h, w) and sample.stride(3) == 1 and style.stride(3) == 1
+    i64 = C.c_int64
+    check(load().dbir_wavelet_fix(_fp(sample), i64(sample.stride(0)), i64(sample.stride(1)), i64(sample.stride(2)),
+                                  _fp(style), i64(style.stride(0)), i64(style.stride(1)), i64(style.stride(2)),
+                                  b, h, w, _fp(out_u8), _fp(out_f32), _sp()), "dbir_wavelet_fix")
+    count_launch()

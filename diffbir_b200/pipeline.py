@@ -11,6 +11,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import lib
 from .model import ControlLDM, Diffusion
 from .sampler import DDIMSampler, SpacedSampler
 from .utils.common import make_tiled_fn, wavelet_reconstruction
@@ -44,6 +45,7 @@ class Pipeline:
         self.device = device
         self.output_size: Tuple[int, int] = None
         self.taps: Optional[dict] = None   # set to {} to capture intermediates (tests)
+        self.fused_post = True             # colour fix + quantisation as one kernel (False: the torch op sequence)
         self.marks: Optional[list] = None  # set to [] to record (phase, CUDA event) boundaries (bench.py phases_ms)
 
     def _mark(self, name: str) -> None:
@@ -173,9 +175,19 @@ class Pipeline:
                                  cldm_tile_stride, pos_prompt, neg_prompt, cfg_scale, start_point_type,
                                  sampler_type, noise_aug, rescale_cfg, s_churn, s_tmin, s_tmax, s_noise,
                                  eta, order, x_T=x_T)
-        sample = F.interpolate(wavelet_reconstruction((sample + 1) / 2, cond_img), size=self.output_size,
-                               mode="bicubic", antialias=True)
-        out = (sample * 255.0).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        if tuple(sample.shape[2:]) == tuple(self.output_size) and sample.is_cuda and self.fused_post:
+            # no resize (antialiased bicubic at scale 1 is the identity): colour fix + x255 / clamp /
+            # truncate + NHWC in one kernel (dbir_wavelet_fix) instead of ~45 full-resolution passes
+            out = torch.empty(sample.shape[0], sample.shape[2], sample.shape[3], 3, dtype=torch.uint8, device=sample.device)
+            lib.wavelet_fix(sample.float(), cond_img.float(), out_u8=out)
+        else:
+            if sample.is_cuda and self.fused_post:
+                fixed = torch.empty(sample.shape, dtype=torch.float32, device=sample.device)
+                lib.wavelet_fix(sample.float(), cond_img.float(), out_f32=fixed)
+            else:
+                fixed = wavelet_reconstruction((sample + 1) / 2, cond_img)
+            sample = F.interpolate(fixed, size=self.output_size, mode="bicubic", antialias=True)
+            out = (sample * 255.0).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
         self._mark("post")
         return out
 

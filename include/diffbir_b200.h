@@ -201,6 +201,17 @@ void dbir_debug_attn_stamps(void* buf);   /* per-CTA clock64 sums of later atten
 int dbir_debug_mma_rate(int32_t n, int32_t b_mn_major, int32_t iters, int32_t a_in_tmem, void* out_cycles,
                         void* stream);
 
+/* ---- fused output epilogue -------------------------------------------------------------
+ * fixed = high_freq((sample + 1) / 2) + low_freq(style): wavelet_reconstruction (utils/common.py:29-77,
+ * 5-level a-trous decomposition, replicate padding) of the decoded sample (NCHW view, [-1, 1]) against
+ * the stage-1 image (NCHW view, [0, 1]); element strides per image / channel / row, unit column stride.
+ * out_u8 != NULL: uint8 NHWC trunc(clamp(fixed * 255, 0, 255)) -- the tail of Pipeline.run
+ * (pipeline.py:306-320) when no resize follows; else out_f32 receives `fixed` as contiguous NCHW fp32.
+ */
+int dbir_wavelet_fix(const float* sample, int64_t s_img, int64_t s_ch, int64_t s_row,
+                     const float* style, int64_t t_img, int64_t t_ch, int64_t t_row,
+                     int32_t batch, int32_t h, int32_t w, void* out_u8, float* out_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -515,3 +515,24 @@ def test_norm_kernels_grouped(L):
         L.layernorm(t[g * rows:(g + 1) * rows], c, rows, c, gam[g * c:(g + 1) * c].contiguous(),
                     bet[g * c:(g + 1) * c].contiguous(), sep, c)
         assert torch.equal(o[g * rows:(g + 1) * rows], sep)
+
+
+@pytest.mark.parametrize("b,h,w", [(1, 512, 512), (2, 200, 333), (1, 40, 50), (1, 17, 1030)])
+def test_wavelet_fix_fused_epilogue(L, b, h, w):
+    """dbir_wavelet_fix vs the reference op sequence (utils/common.py:29-77 + pipeline.py:306-320) as
+    torch ops on the same device: fp32 result to accumulation-order level, uint8 output equal except where
+    fixed*255 sits within rounding of an integer (truncation flips by one there)."""
+    from diffbir_b200.utils.common import wavelet_reconstruction
+    pad_s = torch.empty(b, 3, h + 8, w + 24, device="cuda").uniform_(-1.2, 1.2, generator=g(1))
+    pad_t = torch.empty(b, 3, h + 16, w + 8, device="cuda").uniform_(0, 1, generator=g(2))
+    sample, style = pad_s[:, :, :h, :w], pad_t[:, :, :h, :w]           # strided views, like the pipeline's crops
+    ref = wavelet_reconstruction((sample + 1) / 2, style)
+    out32 = torch.empty(b, 3, h, w, device="cuda")
+    L.wavelet_fix(sample, style, out_f32=out32)
+    assert (out32 - ref).abs().max().item() < 2e-6
+    ref8 = (ref * 255.0).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    out8 = torch.empty(b, h, w, 3, dtype=torch.uint8, device="cuda")
+    L.wavelet_fix(sample, style, out_u8=out8)
+    diff = (out8.int() - ref8.int()).abs()
+    assert diff.max().item() <= 1 and (diff != 0).float().mean().item() < 1e-3
+    assert out8.min().item() == 0 and out8.max().item() == 255        # the clamp is exercised
