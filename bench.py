@@ -109,6 +109,40 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+_CAL = {}
+
+
+def calibrated_threads():
+    """Thread count for the CPU arms: the fastest of {all, 1/2, 1/4 of the host threads, 32} on a short fp32
+    conv + matmul probe. Every schedulable thread is not always the fastest choice (SMT siblings, cgroup
+    CPU quotas below the affinity mask: a 128-thread box ran the oracle 5x slower than a 64-thread one),
+    and the baseline should be the reference's best, not its worst."""
+    if _CAL:
+        return _CAL["best"], _CAL["probe_ms"]
+    import torch
+    import torch.nn.functional as F
+    n = host_threads()
+    cands = sorted({c for c in (n, n // 2, n // 4, 32, 16) if 1 <= c <= n}, reverse=True)
+    x = torch.randn(2, 320, 64, 64)
+    w = torch.randn(320, 320, 3, 3)
+    a = torch.randn(8192, 320)
+    b = torch.randn(320, 1280)
+    res = {}
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            F.conv2d(x, w, padding=1); a @ b
+            t0 = time.perf_counter()
+            for _ in range(3):
+                F.conv2d(x, w, padding=1)
+                a @ b
+            res[c] = (time.perf_counter() - t0) / 3 * 1e3
+    best = min(res, key=res.get)
+    torch.set_num_threads(best)
+    _CAL.update(best=best, probe_ms={str(k): round(v, 2) for k, v in res.items()})
+    return best, _CAL["probe_ms"]
+
+
 # ------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port of the reference on the host cores
 # ------------------------------------------------------------------------------------------
@@ -121,7 +155,7 @@ def cpu_reference_times(n_steps: int = 1, warm: int = 0, size: int = 512):
     from diffbir_b200.utils.synth import make_state_dict, synthetic_lq
     from oracle import cldm as ocl
     from oracle import swinir as osw
-    torch.set_num_threads(host_threads())
+    torch.set_num_threads(calibrated_threads()[0])
     torch.manual_seed(231)
     L = size // 8
     t = {}
@@ -177,9 +211,10 @@ def run_reference(args):
                          "component_seconds": {"swinir": t["swinir"], "vae_encode": t["vae_encode"],
                                                "vae_decode": t["vae_decode"], "sampler_step_median": step_s,
                                                "sampler_steps": t["sampler_step"]},
-                         "note": ("CPU arm, independent of the GPU count: thread count forced to every host core "
-                                  "(torchrun's OMP_NUM_THREADS=1 is overridden); ratios against it are only "
-                                  "meaningful at N=1")},
+                         "thread_probe_ms": calibrated_threads()[1], "host_threads": host_threads(),
+                         "note": ("CPU arm, independent of the GPU count: thread count = the fastest of a short probe over "
+                                  "{all, 1/2, 1/4 of the host threads, 32, 16} (torchrun's OMP_NUM_THREADS=1 is overridden); "
+                                  "ratios against it are only meaningful at N=1")},
         "e2e": {"value": mpix, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -490,6 +525,7 @@ def run_ours(args):
         step_s = t["sampler_step"][0]
         total = cpu_image_seconds(t, step_s)
         cpu = {"value": 512 * 512 / 1e6 / total, "unit": "MPix/s", "cores": cores, "kind": "port",
+               "thread_probe_ms": calibrated_threads()[1], "host_threads": host_threads(),
                "sample": (f"oracle port, fp32: SwinIR {t['swinir']:.2f}s + VAE encode 2x{t['vae_encode']:.2f}s + "
                           f"1 of 50 sampler steps ({step_s:.2f}s, 2 forwards) x50 + VAE decode {t['vae_decode']:.2f}s "
                           f"= {total:.1f}s per 512^2 image (extrapolated)")}

@@ -10,46 +10,75 @@ namespace {
 // ---------------------------------------------------------------------------------------
 // conv3x3, tiny Cin (<= 16), stride 1 pad 1. Input = virtual concat of two NCHW fp32 tensors
 // (ControlNet stem: cat(x, hint), controlnet.py:316). Weights fp32 [9*Cin][Cout]
-// (k = tap*Cin + c). Output NHWC fp32. One thread per (pixel, 4 output channels).
+// (k = tap*Cin + c). Output NHWC fp32.
+// One CTA = a strip of 32 consecutive pixels of one image row: the (Cin x 3 x 34) input patch is
+// staged in shared memory once (scale/shift applied, zero outside the image), then every thread
+// owns 4 output channels of 4 pixels of the strip (p, p+8, p+16, p+24), so each 16-byte weight
+// load (L1-resident, coalesced across the warp) feeds 16 FMAs. The stems run first in every
+// forward of the step loop: the one-thread-per-(pixel, channel quad) version spent 40-75 us there
+// on address arithmetic and one weight load per 4 FMAs.
 // ---------------------------------------------------------------------------------------
+constexpr int SC_STRIP = 32;
 __global__ void __launch_bounds__(256)
 conv3x3_small_cin_kernel(const float* __restrict__ in1, const float* __restrict__ in2, int c1, int c2,
                          int n, int h, int w, const float* __restrict__ wt,
                          const float* __restrict__ bias, int cout, float* __restrict__ out,
                          float in_scale, float in_shift) {
+  __shared__ float s_in[16][3][SC_STRIP + 4];
   pdl_trigger();
-  pdl_wait();
   const int cin = c1 + c2;
   const int cv = cout / 4;
-  const long long total = static_cast<long long>(n) * h * w * cv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int co = static_cast<int>(i % cv) * 4;
-    const long long pix = i / cv;
-    const int x = static_cast<int>(pix % w);
-    const int y = static_cast<int>((pix / w) % h);
-    const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
-    float4 acc = *reinterpret_cast<const float4*>(bias + co);
+  const int strips_x = (w + SC_STRIP - 1) / SC_STRIP;
+  const int x0 = (blockIdx.x % strips_x) * SC_STRIP;
+  const int y = (blockIdx.x / strips_x) % h;
+  const int b = blockIdx.x / (strips_x * h);
+  pdl_wait();
+  for (int i = threadIdx.x; i < cin * 3 * (SC_STRIP + 2); i += blockDim.x) {
+    const int xx = i % (SC_STRIP + 2);
+    const int r = (i / (SC_STRIP + 2)) % 3;
+    const int c = i / (3 * (SC_STRIP + 2));
+    const int gy = y + r - 1, gx = x0 + xx - 1;
+    float v = 0.f;
+    if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+      const float* src = c < c1 ? in1 + ((static_cast<long long>(b) * c1 + c) * h + gy) * w + gx
+                                : in2 + ((static_cast<long long>(b) * c2 + (c - c1)) * h + gy) * w + gx;
+      v = __ldg(src) * in_scale + in_shift;
+    }
+    s_in[c][r][xx] = v;
+  }
+  __syncthreads();
+  const long long row_base = (static_cast<long long>(b) * h + y) * w + x0;
+  for (int i = threadIdx.x; i < (SC_STRIP / 4) * cv; i += blockDim.x) {
+    const int co = (i % cv) * 4;
+    const int pg = i / cv;                       // pixels pg, pg + 8, pg + 16, pg + 24 of the strip
+    const float4 bv = *reinterpret_cast<const float4*>(bias + co);
+    float4 acc[4] = {bv, bv, bv, bv};
     for (int tap = 0; tap < 9; ++tap) {
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+      const int ty = tap / 3, tx = tap - 3 * ty;
+#pragma unroll 4
       for (int c = 0; c < cin; ++c) {
-        const float* src = c < c1 ? in1 + ((static_cast<long long>(b) * c1 + c) * h + yy) * w + xx
-                                  : in2 + ((static_cast<long long>(b) * c2 + (c - c1)) * h + yy) * w + xx;
-        const float v = __ldg(src) * in_scale + in_shift;
-        const float4 wv = *reinterpret_cast<const float4*>(wt + static_cast<long long>(tap * cin + c) * cout + co);
-        acc.x += v * wv.x; acc.y += v * wv.y; acc.z += v * wv.z; acc.w += v * wv.w;
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wt + static_cast<long long>(tap * cin + c) * cout + co));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v = s_in[c][ty][pg + 8 * j + tx];
+          acc[j].x += v * wv.x; acc[j].y += v * wv.y; acc[j].z += v * wv.z; acc[j].w += v * wv.w;
+        }
       }
     }
-    *reinterpret_cast<float4*>(out + pix * cout + co) = acc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (x0 + pg + 8 * j < w)
+        *reinterpret_cast<float4*>(out + (row_base + pg + 8 * j) * cout + co) = acc[j];
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // conv3x3, tiny Cout (<= 8), stride 1 pad 1, op16 NHWC input (already normalised / activated),
-// fp32 weights [Cout][9*Cin]. One warp per output pixel; lanes split K = 9*Cin.
+// fp32 weights [Cout][9*Cin]. One warp per 4 consecutive pixels of a row; lanes split the
+// flattened K = (tap, 8-channel vector) space, each weight vector (L1) is applied to all 4 pixels.
 // out = (acc + bias) * post_scale + post_shift[c]; layout NCHW (out_nchw) or NHWC.
 // ---------------------------------------------------------------------------------------
+constexpr int SO_PX = 4;
 template <int COUT>
 __global__ void __launch_bounds__(256)
 conv3x3_small_cout_kernel(const op_t* __restrict__ in, int n, int h, int w, int cin,
@@ -61,21 +90,37 @@ conv3x3_small_cout_kernel(const op_t* __restrict__ in, int n, int h, int w, int 
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const long long npix = static_cast<long long>(n) * h * w;
-  const int vec_per_tap = cin / 8;                 // 8 x 16-bit = 16 B
-  for (long long pix = warp_global; pix < npix; pix += nwarps) {
-    const int x = static_cast<int>(pix % w);
-    const int y = static_cast<int>((pix / w) % h);
-    const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
-    float acc[COUT];
+  const int groups_x = (w + SO_PX - 1) / SO_PX;
+  const long long ngroups = static_cast<long long>(n) * h * groups_x;
+  const int vpt = cin / 8;                         // 16-byte vectors per tap
+  const int kvec = 9 * vpt;
+  for (long long g = warp_global; g < ngroups; g += nwarps) {
+    const int x0 = static_cast<int>(g % groups_x) * SO_PX;
+    const int y = static_cast<int>((g / groups_x) % h);
+    const int b = static_cast<int>(g / (static_cast<long long>(groups_x) * h));
+    float acc[SO_PX][COUT];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-      const op_t* src = in + ((static_cast<long long>(b) * h + yy) * w + xx) * cin;
-      for (int v = lane; v < vec_per_tap; v += 32) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(src + v * 8);
+    for (int j = 0; j < SO_PX; ++j)
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[j][o] = 0.f;
+    for (int idx = lane; idx < kvec; idx += 32) {
+      const int tap = idx / vpt, v = idx - tap * vpt;
+      const int ty = tap / 3, tx = tap - 3 * ty;
+      const int yy = y + ty - 1;
+      if (yy < 0 || yy >= h) continue;
+      float4 w0[COUT], w1[COUT];
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float* wr = wt + static_cast<long long>(o) * 9 * cin + tap * cin + v * 8;
+        w0[o] = __ldg(reinterpret_cast<const float4*>(wr));
+        w1[o] = __ldg(reinterpret_cast<const float4*>(wr + 4));
+      }
+      const op_t* row = in + (static_cast<long long>(b) * h + yy) * w * cin + v * 8;
+#pragma unroll
+      for (int j = 0; j < SO_PX; ++j) {
+        const int xx = x0 + j + tx - 1;
+        if (xx < 0 || xx >= w) continue;
+        const uint4 raw = *reinterpret_cast<const uint4*>(row + static_cast<long long>(xx) * cin);
         float f[8];
         float2 t;
         t = unpack2(raw.x); f[0] = t.x; f[1] = t.y;
@@ -83,21 +128,24 @@ conv3x3_small_cout_kernel(const op_t* __restrict__ in, int n, int h, int w, int 
         t = unpack2(raw.z); f[4] = t.x; f[5] = t.y;
         t = unpack2(raw.w); f[6] = t.x; f[7] = t.y;
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-          const float* wr = wt + static_cast<long long>(o) * 9 * cin + tap * cin + v * 8;
-          const float4 w0 = *reinterpret_cast<const float4*>(wr);
-          const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-          acc[o] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x +
-                    f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
-        }
+        for (int o = 0; o < COUT; ++o)
+          acc[j][o] += f[0] * w0[o].x + f[1] * w0[o].y + f[2] * w0[o].z + f[3] * w0[o].w + f[4] * w1[o].x +
+                       f[5] * w1[o].y + f[6] * w1[o].z + f[7] * w1[o].w;
       }
     }
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = warp_sum(acc[o]);
-    if (lane == 0) {
+    for (int j = 0; j < SO_PX; ++j)
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[j][o] = warp_sum(acc[j][o]);
+    if (lane < SO_PX && x0 + lane < w) {
+      const int x = x0 + lane;
+      const long long pix = (static_cast<long long>(b) * h + y) * w + x;
 #pragma unroll
       for (int o = 0; o < COUT; ++o) {
-        float v = (acc[o] + bias[o]) * post_scale + (post_shift ? post_shift[o] : 0.f);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < SO_PX; ++j) if (j == lane) s = acc[j][o];
+        const float v = (s + bias[o]) * post_scale + (post_shift ? post_shift[o] : 0.f);
         if (out_nchw) out[((static_cast<long long>(b) * COUT + o) * h + y) * w + x] = v;
         else out[pix * COUT + o] = v;
       }
@@ -173,6 +221,36 @@ linear_f32_kernel(const float* __restrict__ x, long long ldx, int m, int k,
         y[static_cast<long long>(m0 + r) * ldy + n] = v;
       }
     }
+  }
+}
+
+// Same contract for many rows of a tiny feature count (k, n <= 16: the VAE's 1x1 quant convs over
+// every latent pixel, vae.py:569-570): one thread per row, weights broadcast from shared memory.
+// (The warp-per-feature kernel above launches n/8 CTAs and walks the rows serially: 0.8 ms for the
+// 4096 x 4 -> 4 post_quant_conv of one 512^2 image.)
+__global__ void __launch_bounds__(256)
+linear_f32_rows_kernel(const float* __restrict__ x, long long ldx, int m, int k,
+                       const float* __restrict__ wt, const float* __restrict__ bias, int nout,
+                       int silu_in, int silu_out, float* __restrict__ y, long long ldy) {
+  __shared__ float s_w[16 * 16], s_b[16];
+  for (int i = threadIdx.x; i < nout * k; i += blockDim.x) s_w[i] = wt[i];
+  if (threadIdx.x < nout) s_b[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  float xv[16];
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    xv[kk] = kk < k ? x[static_cast<long long>(row) * ldx + kk] : 0.f;
+    if (silu_in) xv[kk] = silu_f(xv[kk]);
+  }
+  for (int o = 0; o < nout; ++o) {
+    float acc = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) if (kk < k) acc += xv[kk] * s_w[o * k + kk];
+    float v = acc + s_b[o];
+    if (silu_out) v = silu_f(v);
+    y[static_cast<long long>(row) * ldy + o] = v;
   }
 }
 
@@ -386,8 +464,9 @@ extern "C" int dbir_conv3x3_small_cin(const float* in1, const float* in2, int32_
                                       float in_shift, float* out_nhwc, void* stream) {
   DBIR_REQUIRE(in1 && weight_kc && bias && out_nhwc, "dbir_conv3x3_small_cin: null pointer");
   DBIR_REQUIRE(c1 + c2 <= 16 && cout % 4 == 0, "dbir_conv3x3_small_cin: Cin<=16, Cout%%4==0");
-  const long long total = static_cast<long long>(n) * h * w * (cout / 4);
-  DBIR_CHECK_CUDA(dbir_launch(conv3x3_small_cin_kernel, dim3(grid_for(total)), dim3(256), 0, ST(stream), in1, in2, c1,
+  const long long strips = static_cast<long long>(n) * h * ((w + SC_STRIP - 1) / SC_STRIP);
+  DBIR_REQUIRE(strips < (1LL << 31), "dbir_conv3x3_small_cin: too many strips");
+  DBIR_CHECK_CUDA(dbir_launch(conv3x3_small_cin_kernel, dim3(static_cast<unsigned>(strips)), dim3(256), 0, ST(stream), in1, in2, c1,
                               c2, n, h, w, weight_kc, bias, cout, out_nhwc, in_scale, in_shift));
   return 0;
 }
@@ -398,8 +477,8 @@ extern "C" int dbir_conv3x3_small_cout(const void* in_nhwc, int32_t n, int32_t h
                                        float* out, int32_t out_nchw, void* stream) {
   DBIR_REQUIRE(in_nhwc && weight && bias && out, "dbir_conv3x3_small_cout: null pointer");
   DBIR_REQUIRE(cin % 8 == 0, "dbir_conv3x3_small_cout: Cin must be a multiple of 8");
-  const long long npix = static_cast<long long>(n) * h * w;
-  const int grid = grid_for(npix * 32);
+  const long long ngroups = static_cast<long long>(n) * h * ((w + SO_PX - 1) / SO_PX);
+  const int grid = grid_for(ngroups * 32);
   const op_t* in = reinterpret_cast<const op_t*>(in_nhwc);
 #define LAUNCH_SC(C)                                                                              \
   DBIR_CHECK_CUDA(dbir_launch(conv3x3_small_cout_kernel<C>, dim3(grid), dim3(256), 0, ST(stream), in, n, h, w, cin, \
@@ -431,6 +510,11 @@ extern "C" int dbir_linear_f32(const float* x, int64_t ldx, int32_t m, int32_t k
                                int32_t silu_in, int32_t silu_out, float* y, int64_t ldy,
                                void* stream) {
   DBIR_REQUIRE(x && weight && y && m > 0 && n > 0 && k > 0, "dbir_linear_f32: bad args");
+  if (k <= 16 && n <= 16 && m >= 256) {
+    linear_f32_rows_kernel<<<(m + 255) / 256, 256, 0, ST(stream)>>>(x, ldx, m, k, weight, bias, n, silu_in, silu_out, y, ldy);
+    DBIR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int warps_per_cta = 8;
   linear_f32_kernel<<<(n + warps_per_cta - 1) / warps_per_cta, 256, 0, ST(stream)>>>(
       x, ldx, m, k, weight, bias, n, silu_in, silu_out, y, ldy);

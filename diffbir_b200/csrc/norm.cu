@@ -135,7 +135,29 @@ gn_stats_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
 
 // Finalisation of statistics whose partial sums were emitted by the producing GEMM epilogues
 // (dbir_gemm gn_partials): grid (32 groups, N), fixed-order fp64 combine.
-__global__ void __launch_bounds__(128)
+constexpr int FIN_THREADS = 256;
+// This thread's share of the (slot, channel) partial pairs of one source, four loads in flight per
+// round: the kernel is a dependent link of every GroupNorm chain and was bound by the L2 latency of
+// its one-load-at-a-time loop, not by bytes (fixed order per thread => deterministic).
+__device__ __forceinline__ void fin_accumulate(const float* __restrict__ base, int c, int lo, int w, int total,
+                                               double& a, double& b) {
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * FIN_THREADS) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * FIN_THREADS;
+      v[u] = make_float2(0.f, 0.f);
+      if (i < total) {
+        const int sl = i / w, cc = lo + i % w;
+        v[u] = __ldcg(reinterpret_cast<const float2*>(base + (static_cast<long long>(sl) * c + cc) * 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a += v[u].x; b += v[u].y; }
+  }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
 gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float* __restrict__ p2,
                    int slots2, int c2, int hw, float eps, float* __restrict__ stats) {
   pdl_trigger();
@@ -149,33 +171,30 @@ gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float
     const int lo = min(ch0, c1), hi = min(ch1, c1), w = hi - lo;
     const int total = w * slots1;
     const float* base = p1 + static_cast<long long>(n) * slots1 * c1 * 2;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int sl = i / w, cc = lo + i % w;
-      const float2 v = *reinterpret_cast<const float2*>(base + (static_cast<long long>(sl) * c1 + cc) * 2);
-      a += v.x; b += v.y;
-    }
+    fin_accumulate(base, c1, lo, w, total, a, b);
   }
   if (c2 > 0) {
     const int lo = max(ch0, c1) - c1, hi = max(ch1, c1) - c1, w = hi - lo;
     const int total = w * slots2;
     const float* base = p2 + static_cast<long long>(n) * slots2 * c2 * 2;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int sl = i / w, cc = lo + i % w;
-      const float2 v = *reinterpret_cast<const float2*>(base + (static_cast<long long>(sl) * c2 + cc) * 2);
-      a += v.x; b += v.y;
-    }
+    fin_accumulate(base, c2, lo, w, total, a, b);
   }
-  __shared__ double sa[128], sb[128];
-  sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+  // fixed-order tree: xor-shuffles inside each warp, then thread 0 adds the 8 warp sums in warp order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  __shared__ double sa[FIN_THREADS / 32], sb[FIN_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int i = 0; i < FIN_THREADS / 32; ++i) { ta += sa[i]; tb += sb[i]; }
     const double cnt = static_cast<double>(hw) * cpg;
-    const double mean = sa[0] / cnt;
-    double var = sb[0] / cnt - mean * mean;
+    const double mean = ta / cnt;
+    double var = tb / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
     stats[(n * 32 + g) * 2 + 0] = static_cast<float>(mean);
     stats[(n * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -352,7 +371,7 @@ extern "C" int dbir_gn_finalize(const float* partials1, int32_t slots1, int32_t 
                                 void* stream) {
   DBIR_REQUIRE(partials1 && stats && slots1 > 0 && (c1 + c2) % 32 == 0, "dbir_gn_finalize: bad args");
   DBIR_REQUIRE(c2 == 0 || (partials2 && slots2 > 0), "dbir_gn_finalize: second source missing");
-  DBIR_CHECK_CUDA(dbir_launch(gn_finalize_kernel, dim3(32, n), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream),
+  DBIR_CHECK_CUDA(dbir_launch(gn_finalize_kernel, dim3(32, n), dim3(FIN_THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
                               partials1, slots1, c1, partials2, slots2, c2, hw, eps, stats));
   return 0;
 }

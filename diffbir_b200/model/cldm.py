@@ -44,6 +44,7 @@ class ControlLDM:
         self._tokenizer = None
         self._ctx_ref = None      # (tensor, version) the engine's cross-attention K/V were built from
         self._t_key = None
+        self._txt_cache: Dict[str, torch.Tensor] = {}   # prompt -> [77, D] text-tower output (see encode_text)
 
     # --------------------------------------------------------------- checkpoint loaders
     @torch.no_grad()
@@ -85,6 +86,7 @@ class ControlLDM:
     def _invalidate(self):
         self.engine = self.vae = self.clip = None
         self._ctx_ref = self._t_key = None
+        self._txt_cache = {}
 
     def _build(self):
         if self.engine is None:
@@ -127,6 +129,24 @@ class ControlLDM:
                     "(or construct ControlLDM(synthetic_tokenizer=True) for synthetic checkpoints)")
         return self._tokenizer(txt)
 
+    TXT_CACHE_MAX = 64
+
+    @torch.no_grad()
+    def encode_text(self, txt: List[str]) -> torch.Tensor:
+        """FrozenOpenCLIPEmbedder.forward (model/clip.py:56-61) -> fp32 [len(txt), 77, D]. The output is a
+        pure function of the prompt string and the frozen weights, so it is kept per prompt: a folder of
+        images restored with the same positive / negative prompt (the CLI default) runs the text tower
+        once instead of twice per image. Distinct new prompts of one call share one batched tower pass."""
+        self._build()
+        new = [t for t in dict.fromkeys(txt) if t not in self._txt_cache]
+        if new:
+            emb = self.clip(self.tokenize(new))
+            if len(self._txt_cache) + len(new) > self.TXT_CACHE_MAX:
+                self._txt_cache.clear()
+            for t, e in zip(new, emb):
+                self._txt_cache[t] = e.clone()
+        return torch.stack([self._txt_cache[t] for t in txt], 0)
+
     @torch.no_grad()
     def vae_encode(self, image: torch.Tensor, sample: bool = True, tiled: bool = False,
                    tile_size: int = -1) -> torch.Tensor:
@@ -151,7 +171,7 @@ class ControlLDM:
     def prepare_condition(self, cond_img: torch.Tensor, txt: List[str], tiled: bool = False,
                           tile_size: int = -1) -> Dict[str, torch.Tensor]:
         self._build()
-        return dict(c_txt=self.clip(self.tokenize(txt)),
+        return dict(c_txt=self.encode_text(list(txt)),
                     c_img=self.vae_encode(cond_img * 2 - 1, sample=False, tiled=tiled, tile_size=tile_size))
 
     @torch.no_grad()
@@ -161,7 +181,7 @@ class ControlLDM:
         prompt lists share one batched text-tower call."""
         self._build()
         n = len(pos_txt)
-        c_txt = self.clip(self.tokenize(list(pos_txt) + list(neg_txt)))
+        c_txt = self.encode_text(list(pos_txt) + list(neg_txt))
         c_img = self.vae_encode(cond_img * 2 - 1, sample=False)
         return (dict(c_txt=c_txt[:n].contiguous(), c_img=c_img),
                 dict(c_txt=c_txt[n:].contiguous(), c_img=c_img.clone()))

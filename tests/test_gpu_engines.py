@@ -55,14 +55,20 @@ def test_cldm_small_vs_oracle_shapes(L, nb):
     hint = torch.randn(nb, 4, L, L, generator=gen).cuda()
     ctx = torch.randn(nb, 77, UNET_SMALL["context_dim"], generator=gen).cuda()
     scales = [1.0] * 13
+    import time
+    t0 = time.perf_counter()
     eng.set_context(ctx)
     eng.set_timesteps([500], nb=nb)
     eng.load_step(0)
     eps = eng.forward(x, hint, scales)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     with torch.no_grad():
         ref = ocl.cldm_forward(to_dev(usd), to_dev(csd), x, torch.full((nb,), 500, device="cuda"), ctx, hint, scales)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
     e = rel_rms(eps, ref)
-    print(f"cldm small L={L} nb={nb}: rel rms {e:.2e}")
+    print(f"cldm small L={L} nb={nb}: rel rms {e:.2e} (engine {t1 - t0:.1f}s incl. plan tuning, oracle {t2 - t1:.1f}s)")
     assert e < TOL
 
 
