@@ -19,6 +19,8 @@ cond/uncond) -> VAE decode -> colour fix -> uint8.  Random-init SD-2.1 / SwinIR 
              the ranks, one NCCL all-gather of the per-tile eps per step, every rank blends + updates
              the full latent. Its MPix/s across N is the STRONG-scaling curve of the path that has a
              collective; `value` stays the 512^2 replica throughput (weak scaling, no collective).
+  v21_1024_b4 : EVERY line also restores ONE batch of 4 1024^2 images with the v2.1 settings (configs[4]); at N > 1
+             the 8 (image, CFG branch) forwards of a step are sharded over the ranks (all-gather of eps per step)
   phases_ms : CUDA-event time of each pipeline stage of the 512^2 image
   gpu_torch_baseline : the reference algorithm (oracle port) as stock PyTorch kernels on the same
              GPU, fp16 autocast, bounded sample -- informational (SURVEY 8d "GPU baseline")
@@ -474,6 +476,57 @@ def run_ours(args):
                  "workload": "Tiled BSR 2048x2048, tile 512 stride 256: 49 latent tiles sharded round-robin over the ranks, "
                              "one NCCL all-gather of per-tile eps per step (configs[3]); SwinIR / VAE / CLIP replicated"}
 
+    # ------------------------------------------------------------------ v2.1 1024^2 batch 4 (configs[4])
+    v21 = None
+    if not args.no_v21:
+        from diffbir_b200.model import Diffusion
+        B5 = 4
+        vkw = dict(RUN_DEFAULTS, pos_prompt="a photo of a mountain lake at sunrise, highly detailed, sharp focus")
+        lq5 = synthetic_lq(1024, 1024, batch=B5, seed=5)           # the same 4 images on every rank
+        lq5_pinned = torch.from_numpy(lq5).pin_memory()
+        lq5_dev = lq5_pinned.to(dev)
+        eps_diffusion, pipe.diffusion = pipe.diffusion, Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000,
+                                                                  parameterization="v", zero_snr=True)
+        pipe.shard_batch = world > 1
+        torch.manual_seed(231)
+        pipe.run_device(lq5_dev, **dict(vkw, steps=3))             # warm-up: plans, graphs, NCCL
+        barrier()
+        sampler_mod.Sampler.time_collective = True
+        pipe.marks = []
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.manual_seed(231)
+        b0.record()
+        pipe.run_device(lq5_dev, **vkw)
+        b1.record()
+        barrier()
+        v_ms = b0.elapsed_time(b1)
+        vphases = pipe.phases_ms()
+        vstats = dict(pipe.last_sampler.last_stats)
+        vag = [a.elapsed_time(b) for a, b in vstats.get("allgather_events", [])]
+        pipe.marks = None
+        sampler_mod.Sampler.time_collective = False
+        barrier()
+        w0 = time.perf_counter()
+        torch.manual_seed(231)
+        out5 = pipe.run(lq5_pinned, **vkw)
+        torch.cuda.synchronize()
+        v_e2e_ms = (time.perf_counter() - w0) * 1e3
+        barrier()
+        pipe.shard_batch = False
+        pipe.diffusion = eps_diffusion
+        v_ms, v_e2e_ms, v_loop, v_ag = reduce_max([v_ms, v_e2e_ms, vphases.get("sampler_loop", 0.0),
+                                                   (sum(vag) / len(vag)) if vag else 0.0])
+        mp5 = B5 * 1024 * 1024 / 1e6
+        v21 = {"value": mp5 / (v_ms / 1e3), "unit": "MPix/s", "scaling": "strong", "ms_per_batch": v_ms,
+               "e2e": {"value": mp5 / (v_e2e_ms / 1e3), "unit": "MPix/s", "h2d_bytes_per_step": int(lq5.nbytes),
+                       "d2h_bytes_per_step": int(out5.nbytes)},
+               "forwards_per_step_rank0": int(vstats.get("forwards_per_step", 0)), "forwards_per_step_total": 2 * B5,
+               "allgather_ms_per_step": v_ag, "sampler_loop_ms": v_loop, "phases_ms_rank0": vphases,
+               "workload": "v2.1 (v-parameterization, zero terminal SNR) caption-conditioned BSR 1024x1024, 50-step spaced, cfg 4.0, "
+                           "batch 4: the 8 (image, CFG branch) forwards of a step sharded round-robin over the ranks, one NCCL "
+                           "all-gather of eps per step (configs[4]); SwinIR / VAE / CLIP replicated; fp16 operands (the bf16 "
+                           "build is DBIR_OPERANDS=bf16)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -547,6 +600,7 @@ def run_ours(args):
         "clocks": clk,
         "phases_ms": phases,
         "tiled2048": tiled,
+        "v21_1024_b4": v21,
         "roofline": roof,
         "cpu_baseline": cpu,
         "gpu_torch_baseline": gpu_base,
@@ -572,6 +626,7 @@ def main():
     ap.add_argument("--workload", default="512", choices=["512", "tiled2048"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and GPU-torch baseline legs")
     ap.add_argument("--no-tiled", action="store_true", help="skip the tiled-2048 block")
+    ap.add_argument("--no-v21", action="store_true", help="skip the v2.1 1024^2 batch-4 block")
     ap.add_argument("--tiled-images", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":

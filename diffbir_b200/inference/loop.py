@@ -20,7 +20,8 @@ from ..utils.common import instantiate_from_config
 from .pretrained_models import default_weights_dir, resolve
 
 CONFIG_DIR = Path(__file__).resolve().parents[2] / "configs" / "inference"
-SUPPORTED_SAMPLERS = ("spaced", "ddim")
+SUPPORTED_SAMPLERS = ("dpm++_m2", "spaced", "ddim", "edm_euler", "edm_euler_a", "edm_heun", "edm_dpm_2", "edm_dpm_2_a", "edm_lms",
+                      "edm_dpm++_2s_a", "edm_dpm++_sde", "edm_dpm++_2m", "edm_dpm++_2m_sde", "edm_dpm++_3m_sde")
 
 
 def load_config(name: str) -> dict:
@@ -83,8 +84,7 @@ def check_supported(args: Namespace) -> None:
     if args.device != "cuda":
         raise NotImplementedError(f"--device {args.device}: the engines are CUDA (sm_100a) only, there is no CPU path")
     if args.sampler not in SUPPORTED_SAMPLERS:
-        raise NotImplementedError(f"--sampler {args.sampler}: only {SUPPORTED_SAMPLERS} are on the accelerated path "
-                                  "(EDM / DPM-Solver samplers: SURVEY.md §8f)")
+        raise NotImplementedError(f"--sampler {args.sampler}: not one of {SUPPORTED_SAMPLERS}")
     if args.captioner != "none":
         raise NotImplementedError(f"--captioner {args.captioner}: captioners are outside the path; pass --captioner none "
                                   "and a --pos_prompt")

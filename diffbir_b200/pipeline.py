@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from . import lib
 from .model import ControlLDM, Diffusion
-from .sampler import DDIMSampler, SpacedSampler
+from .sampler import DDIMSampler, DPMSolverSampler, EDMSampler, SpacedSampler
 from .utils.common import make_tiled_fn, wavelet_reconstruction
 
 
@@ -46,6 +46,7 @@ class Pipeline:
         self.output_size: Tuple[int, int] = None
         self.taps: Optional[dict] = None   # set to {} to capture intermediates (tests)
         self.fused_post = True             # colour fix + quantisation as one kernel (False: the torch op sequence)
+        self.shard_batch = False           # un-tiled batches: shard (image, CFG branch) forwards over torch.distributed ranks
         self.marks: Optional[list] = None  # set to [] to record (phase, CUDA event) boundaries (bench.py phases_ms)
 
     def _mark(self, name: str) -> None:
@@ -115,8 +116,13 @@ class Pipeline:
             sampler = SpacedSampler(betas, parameterization, rescale_cfg)
         elif sampler_type == "ddim":
             sampler = DDIMSampler(betas, parameterization, rescale_cfg, eta=0)
+        elif sampler_type.startswith("dpm"):
+            sampler = DPMSolverSampler(betas, parameterization, rescale_cfg, sampler_type)
+        elif sampler_type.startswith("edm"):
+            sampler = EDMSampler(betas, parameterization, rescale_cfg, sampler_type, s_churn, s_tmin, s_tmax, s_noise, eta, order)
         else:
-            raise NotImplementedError(f"{sampler_type}: only the spaced and DDIM samplers are on the B200 hot path")
+            raise NotImplementedError(sampler_type)
+        sampler.shard_batch = self.shard_batch
         z = sampler.sample(model=self.cldm, device=self.device, steps=steps, x_size=(bs, 4, h2, w2),
                            cond=cond, uncond=uncond, cfg_scale=cfg_scale, tiled=cldm_tiled,
                            tile_size=cldm_tile_size // 8, tile_stride=cldm_tile_stride // 8, x_T=x_T,

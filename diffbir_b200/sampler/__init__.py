@@ -1,3 +1,5 @@
-from .sampler import DDIMSampler, SpacedSampler, space_timesteps
+from .dpm import DPMSolverSampler
+from .edm import EDMSampler
+from .sampler import DDIMSampler, EngineEval, Sampler, SpacedSampler, space_timesteps
 
-__all__ = ["SpacedSampler", "DDIMSampler", "space_timesteps"]
+__all__ = ["SpacedSampler", "DDIMSampler", "EDMSampler", "DPMSolverSampler", "Sampler", "EngineEval", "space_timesteps"]

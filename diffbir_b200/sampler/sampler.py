@@ -59,6 +59,13 @@ def assemble_gathered(recv: torch.Tensor) -> torch.Tensor:
     return recv.permute(*perm).reshape(nbr, slots * world, *rest).contiguous()
 
 
+def assemble_units(recv: torch.Tensor, num_units: int) -> torch.Tensor:
+    """all_gather output [world, slots, ...] of round-robin owned units -> [num_units, ...] in unit order
+    (unit u = slot*world + rank; the tail entries are padding)."""
+    world, slots = recv.shape[:2]
+    return recv.transpose(0, 1).reshape(slots * world, *recv.shape[2:])[:num_units].contiguous()
+
+
 def _sync_from_rank0(t: torch.Tensor, dev) -> torch.Tensor:
     import torch.distributed as dist
     t = t.to(dev).contiguous()
@@ -80,6 +87,179 @@ def _sync_rng_from_rank0(dev) -> None:
         torch.set_rng_state(st)
 
 
+def tiled_callable(model, tile_size: int, tile_stride: int):
+    """model(x, t, cond) evaluated on Gaussian-weighted sliding latent tiles, accumulated in row-major tile
+    order and normalised — the wrapper every reference sampler puts around model.forward when `tiled`
+    (spaced_sampler.py:204-219 with utils/common.py:172-232)."""
+    def fwd(xx, tt, cd):
+        out = torch.zeros_like(xx)
+        cnt = torch.zeros_like(xx)
+        w = torch.tensor(gaussian_weights(tile_size, tile_size)[None, None], dtype=xx.dtype, device=xx.device)
+        for a, b, c, d in sliding_windows(xx.shape[2], xx.shape[3], tile_size, tile_stride):
+            out[..., a:b, c:d] += model(xx[..., a:b, c:d], tt, {"c_txt": cd["c_txt"], "c_img": cd["c_img"][..., a:b, c:d]}) * w
+            cnt[..., a:b, c:d] += w
+        return out / cnt
+    return fwd
+
+
+class EngineEval:
+    """Everything between a sampler loop and the kernel engine (shared by the spaced / DDIM loops here and the
+    EDM / DPM-Solver samplers): conditioning set-up, ONE batched forward over (CFG branches x images | tiles)
+    captured in a CUDA graph and replayed per evaluation, tile gather / Gaussian blend in the reference's
+    accumulation order, and - with torch.distributed initialised - tiles (tiled sampling) or (branch, image)
+    units (shard_batch) sharded round-robin over the ranks and re-assembled by one all-gather per evaluation.
+
+        ev = EngineEval(model, x_T, cond, uncond, tiled, tile_size, tile_stride)
+        ev.set_timesteps([999, 979, ...])      # every model timestep the loop will ask for (floats allowed)
+        e_cond, e_uncond = ev.eps(x, k)        # model output at timesteps[k]; views of internal buffers
+
+    `ev.x0` is x_T on the engine's device (rank 0's copy when sharded: every rank must hold the same latent,
+    condition and noise stream, otherwise tiles of diverging latents would be blended silently)."""
+
+    def __init__(self, model, x_T, cond, uncond, tiled=False, tile_size=-1, tile_stride=-1, *, shard_tiles=True,
+                 shard_batch=False, time_collective=False):
+        import torch.distributed as dist
+        model._build()
+        self.model, self.eng = model, model.engine
+        eng = self.eng
+        dev = self.dev = eng.dev
+        x = x_T.to(dev, torch.float32).contiguous().clone()
+        B, C, H, W = x.shape
+        self.shape = (B, C, H, W)
+        self.use_cfg = uncond is not None
+        conds = [cond, uncond] if self.use_cfg else [cond]
+        nbr = self.nbr = len(conds)
+        self.tiled, self.time_collective = bool(tiled), time_collective
+        sharded = (shard_tiles if tiled else shard_batch) and dist.is_available() and dist.is_initialized()
+        world, rank = (dist.get_world_size(), dist.get_rank()) if sharded else (1, 0)
+        self.world, self.dist = world, dist
+        if world > 1:
+            x = _sync_from_rank0(x, dev)
+            conds = [dict(cd, c_img=_sync_from_rank0(cd["c_img"].to(dev, torch.float32).contiguous(), dev))
+                     for cd in conds]
+            _sync_rng_from_rank0(dev)
+        self.x0 = x
+        T = Tl = 0
+        if tiled:
+            wins = sliding_windows(H, W, tile_size, tile_stride)
+            T = self.T = len(wins)
+            self.all_coords = torch.tensor([[a, c] for a, _, c, _ in wins], dtype=torch.int32, device=dev)
+            mine = tiles_of_rank(T, rank, world)               # round-robin tile ownership (may be empty: T < world)
+            slots = tile_slots(T, world)
+            Tl, ts_ = len(mine), tile_size
+            self.Tl, self.ts = Tl, ts_
+            self.my_coords = self.all_coords[mine].contiguous() if Tl else self.all_coords[:0]
+            self.wts = torch.tensor(gaussian_weights(ts_, ts_), dtype=torch.float32, device=dev)
+            nb = nbr * Tl * B
+            c_img = torch.empty(nbr, Tl * B, C, ts_, ts_, device=dev)
+            for j, cd in enumerate(conds):
+                if Tl:
+                    lib.tile_gather(cd["c_img"].to(dev, torch.float32).contiguous(), B, C, H, W, self.my_coords,
+                                    Tl, ts_, c_img[j])
+            c_img = c_img.view(nb, C, ts_, ts_)
+            ctx = torch.cat([cd["c_txt"].to(dev, torch.float32).repeat(Tl, 1, 1) for cd in conds], 0)
+            gh = gw = ts_
+            self.send = torch.zeros(nbr, slots, B, C, ts_, ts_, device=dev)
+            self.recv = torch.empty(world, nbr, slots, B, C, ts_, ts_, device=dev) if world > 1 else None
+            self.eps_full = torch.empty(nbr, B, C, H, W, device=dev)
+        elif world > 1:
+            # batch sharding: unit u = branch * B + image, owned round-robin like tiles (u % world)
+            U = nbr * B
+            mine = tiles_of_rank(U, rank, world)
+            slots, nb = tile_slots(U, world), len(mine)
+            all_c_img = torch.cat([cd["c_img"].to(dev, torch.float32) for cd in conds], 0)
+            all_ctx = torch.cat([cd["c_txt"].to(dev, torch.float32).expand(B, -1, -1) for cd in conds], 0)
+            sel = torch.tensor(mine, dtype=torch.long, device=dev)
+            c_img = all_c_img.index_select(0, sel).contiguous()
+            ctx = all_ctx.index_select(0, sel).contiguous()
+            self.img_of_unit = torch.tensor([u % B for u in mine], dtype=torch.long, device=dev)
+            gh, gw = H, W
+            self.send = torch.zeros(slots, C, H, W, device=dev)
+            self.recv = torch.empty(world, slots, C, H, W, device=dev)
+        else:
+            nb = nbr * B
+            c_img = torch.cat([cd["c_img"].to(dev, torch.float32) for cd in conds], 0).contiguous()
+            ctx = torch.cat([cd["c_txt"].to(dev, torch.float32) for cd in conds], 0)
+            gh, gw = H, W
+        self.nb, self.gh, self.gw = nb, gh, gw
+        self._c_img, self._ctx = c_img, ctx
+        self.scales = [float(s) for s in model.control_scales]
+        # Tiled / sharded sampling pins the batch-invariant kernel plans (no split-K, whole attention tiles
+        # per CTA): a sample's eps then has the same bits whatever the per-rank batch is, so the sharded
+        # run is bit-identical to the single-rank run (SURVEY §8e).
+        eng.batch_invariant = bool(tiled) or world > 1 or eng.deterministic
+        self.graph = None
+        self.stats = dict(world=world, tiles=T, tiles_this_rank=Tl, forwards_per_step=nb,
+                          batch_sharded=bool(world > 1 and not tiled))
+
+    def set_timesteps(self, model_ts) -> None:
+        """Time embeddings of every timestep the loop will evaluate + the CUDA graph of the forward."""
+        eng = self.eng
+        self.model_ts = list(model_ts)
+        if self.nb > 0:
+            B, C, H, W = self.shape
+            eng.set_context(self._ctx)
+            eng.set_timesteps(self.model_ts, self.nb)
+            self.model._ctx_ref = self.model._t_key = None      # generic-path caches are now stale
+            eng.load_step(0)
+            self.graph, self.x_in, c_img_buf, self.out, self.graph_launches = eng.graphed_forward(
+                self.nb, C, self.gh, self.gw, self.scales)
+            c_img_buf.copy_(self._c_img)
+
+    def _fill_inputs(self, x: torch.Tensor) -> None:
+        B, C, H, W = self.shape
+        nbr = self.nbr
+        if self.tiled:
+            v = self.x_in.view(nbr, self.Tl * B, C, self.ts, self.ts)
+            lib.tile_gather(x, B, C, H, W, self.my_coords, self.Tl, self.ts, v[0])
+            for j in range(1, nbr):
+                v[j].copy_(v[0])
+        elif self.world > 1:
+            torch.index_select(x, 0, self.img_of_unit, out=self.x_in)
+        else:
+            v = self.x_in.view(nbr, B, C, H, W)
+            for j in range(nbr):
+                v[j].copy_(x)
+
+    def _all_gather(self) -> None:
+        if self.time_collective:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        self.dist.all_gather_into_tensor(self.recv, self.send)
+        if self.time_collective:
+            ev1.record()
+            self.stats.setdefault("allgather_events", []).append((ev0, ev1))
+
+    def eps(self, x: torch.Tensor, step_idx: int):
+        """(cond, uncond | None) model outputs for the full latent x at model_ts[step_idx], fp32 [B,C,H,W]."""
+        B, C, H, W = self.shape
+        nbr, world = self.nbr, self.world
+        if self.nb > 0:
+            self.eng.load_step(step_idx)
+            self._fill_inputs(x)
+            self.graph.replay()
+            lib.count_launch(self.graph_launches)
+        if self.tiled:
+            if world > 1:
+                if self.Tl:
+                    self.send[:, :self.Tl].copy_(self.out.view(nbr, self.Tl, B, C, self.ts, self.ts))
+                self._all_gather()
+                tiles = assemble_gathered(self.recv)             # global tile order, padding at the end
+            else:
+                tiles = self.out.view(nbr, self.Tl, B, C, self.ts, self.ts)
+            for j in range(nbr):
+                lib.tile_blend(tiles[j], B, C, H, W, self.all_coords, self.T, self.ts, self.wts, self.eps_full[j])
+            ev = self.eps_full
+        elif world > 1:
+            if self.nb:
+                self.send[:self.nb].copy_(self.out)
+            self._all_gather()
+            ev = assemble_units(self.recv, nbr * B).view(nbr, B, C, H, W)
+        else:
+            ev = self.out.view(nbr, B, C, H, W)
+        return ev[0], (ev[1] if self.use_cfg else None)
+
+
 class Sampler:
     time_collective = False        # record CUDA events around the per-step all-gather (bench.py sets it)
 
@@ -90,6 +270,10 @@ class Sampler:
         self.parameterization = parameterization
         self.rescale_cfg = rescale_cfg
         self.shard_tiles = True     # tiled sampling: shard tiles over torch.distributed ranks
+        # un-tiled sampling of a batch: shard the (CFG branch, image) forwards over the ranks with one
+        # all-gather of eps per step (BASELINE configs[4]: 4 images x 2 branches -> one forward per GPU of
+        # an 8-GPU box). Opt-in: ranks that restore DIFFERENT images (independent replicas) must not shard.
+        self.shard_batch = False
         self.last_stats: dict = {}
 
     def get_cfg_scale(self, default_cfg_scale: float, model_t: int) -> float:
@@ -126,108 +310,18 @@ class Sampler:
     # ---- kernel-engine path -----------------------------------------------------------------
     def _sample_engine(self, model, ts, coefs, mode, x_T, cond, uncond, cfg_scale, tiled, tile_size,
                        tile_stride):
-        model._build()
-        eng = model.engine
-        dev = eng.dev
-        x = x_T.to(dev, torch.float32).contiguous().clone()
-        B, C, H, W = x.shape
         use_cfg = not (uncond is None or cfg_scale == 1.0)
-        conds = [cond, uncond] if use_cfg else [cond]
-        nbr = len(conds)
-        coefs = coefs.to(dev)
+        ev = EngineEval(model, x_T, cond, uncond if use_cfg else None, tiled, tile_size, tile_stride,
+                        shard_tiles=self.shard_tiles, shard_batch=self.shard_batch, time_collective=self.time_collective)
+        x = ev.x0
+        coefs = coefs.to(ev.dev)
         order = list(range(len(ts)))[::-1]                     # table index of each loop iteration
         model_ts = [int(ts[i]) for i in order]
-
-        import torch.distributed as dist
-        world, rank = ((dist.get_world_size(), dist.get_rank())
-                       if (tiled and self.shard_tiles and dist.is_available() and dist.is_initialized()) else (1, 0))
-        if world > 1:
-            # Every rank must hold the same latent, condition and noise stream: rank 0's are authoritative
-            # (ranks seeded differently would otherwise blend tiles of diverging latents silently).
-            x = _sync_from_rank0(x, dev)
-            conds = [dict(cd, c_img=_sync_from_rank0(cd["c_img"].to(dev, torch.float32).contiguous(), dev))
-                     for cd in conds]
-            _sync_rng_from_rank0(dev)
-
-        if tiled:
-            wins = sliding_windows(H, W, tile_size, tile_stride)
-            T = len(wins)
-            all_coords = torch.tensor([[a, c] for a, _, c, _ in wins], dtype=torch.int32, device=dev)
-            mine = tiles_of_rank(T, rank, world)               # round-robin tile ownership (may be empty: T < world)
-            slots = tile_slots(T, world)
-            Tl, ts_ = len(mine), tile_size
-            my_coords = all_coords[mine].contiguous() if Tl else all_coords[:0]
-            wts = torch.tensor(gaussian_weights(ts_, ts_), dtype=torch.float32, device=dev)
-            nb = nbr * Tl * B
-            c_img = torch.empty(nbr, Tl * B, C, ts_, ts_, device=dev)
-            for j, cd in enumerate(conds):
-                if Tl:
-                    lib.tile_gather(cd["c_img"].to(dev, torch.float32).contiguous(), B, C, H, W, my_coords,
-                                    Tl, ts_, c_img[j])
-            c_img = c_img.view(nb, C, ts_, ts_)
-            ctx = torch.cat([cd["c_txt"].to(dev, torch.float32).repeat(Tl, 1, 1) for cd in conds], 0)
-            gh = gw = ts_
-            send = torch.zeros(nbr, slots, B, C, ts_, ts_, device=dev)
-            recv = torch.empty(world, nbr, slots, B, C, ts_, ts_, device=dev) if world > 1 else None
-            eps_full = torch.empty(nbr, B, C, H, W, device=dev)
-        else:
-            nb = nbr * B
-            c_img = torch.cat([cd["c_img"].to(dev, torch.float32) for cd in conds], 0).contiguous()
-            ctx = torch.cat([cd["c_txt"].to(dev, torch.float32) for cd in conds], 0)
-            gh, gw = H, W
-        scales = [float(s) for s in model.control_scales]
-        # Tiled sampling pins the batch-invariant kernel plans (no split-K, whole attention tiles per
-        # CTA): a tile's eps then has the same bits whatever the per-rank batch is, so the sharded run
-        # is bit-identical to the single-rank run.
-        eng.batch_invariant = bool(tiled) or eng.deterministic
-        if nb > 0:
-            eng.set_context(ctx)
-            eng.set_timesteps(model_ts, nb)
-            model._ctx_ref = model._t_key = None                # generic-path caches are now stale
-            eng.load_step(0)
-            graph, x_in, c_img_buf, eps, graph_launches = eng.graphed_forward(nb, C, gh, gw, scales)
-            c_img_buf.copy_(c_img)
-
-        def fill_inputs():
-            if tiled:
-                v = x_in.view(nbr, Tl * B, C, ts_, ts_)
-                lib.tile_gather(x, B, C, H, W, my_coords, Tl, ts_, v[0])
-                for j in range(1, nbr):
-                    v[j].copy_(v[0])
-            else:
-                v = x_in.view(nbr, B, C, H, W)
-                for j in range(nbr):
-                    v[j].copy_(x)
-
+        ev.set_timesteps(model_ts)
         x_next = torch.empty_like(x)
-        self.last_stats = dict(world=world, tiles=(T if tiled else 0), tiles_this_rank=(Tl if tiled else 0),
-                               forwards_per_step=nb)
+        self.last_stats = ev.stats
         for it, tab_idx in enumerate(order):
-            if nb > 0:
-                eng.load_step(it)
-                fill_inputs()
-                graph.replay()
-                lib.count_launch(graph_launches)
-            if tiled:
-                if world > 1:
-                    if Tl:
-                        send[:, :Tl].copy_(eps.view(nbr, Tl, B, C, ts_, ts_))
-                    if self.time_collective:
-                        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        ev0.record()
-                    dist.all_gather_into_tensor(recv, send)
-                    if self.time_collective:
-                        ev1.record()
-                        self.last_stats.setdefault("allgather_events", []).append((ev0, ev1))
-                    tiles = assemble_gathered(recv)             # global tile order, padding at the end
-                else:
-                    tiles = eps.view(nbr, Tl, B, C, ts_, ts_)
-                for j in range(nbr):
-                    lib.tile_blend(tiles[j], B, C, H, W, all_coords, T, ts_, wts, eps_full[j])
-                e_c, e_u = eps_full[0], (eps_full[1] if use_cfg else None)
-            else:
-                ev = eps.view(nbr, B, C, H, W)
-                e_c, e_u = ev[0], (ev[1] if use_cfg else None)
+            e_c, e_u = ev.eps(x, it)
             noise = torch.randn_like(x)
             cur_cfg = self.get_cfg_scale(cfg_scale, model_ts[it])
             if cur_cfg == 1.0:
@@ -242,16 +336,7 @@ class Sampler:
         x = x_T
         dev = x.device
         coefs = coefs.to(dev)
-        fwd = model
-        if tiled:
-            def fwd(xx, tt, cd):
-                out = torch.zeros_like(xx)
-                cnt = torch.zeros_like(xx)
-                w = torch.tensor(gaussian_weights(tile_size, tile_size)[None, None], dtype=xx.dtype, device=dev)
-                for a, b, c, d in sliding_windows(xx.shape[2], xx.shape[3], tile_size, tile_stride):
-                    out[..., a:b, c:d] += model(xx[..., a:b, c:d], tt, {"c_txt": cd["c_txt"], "c_img": cd["c_img"][..., a:b, c:d]}) * w
-                    cnt[..., a:b, c:d] += w
-                return out / cnt
+        fwd = tiled_callable(model, tile_size, tile_stride) if tiled else model
         for tab_idx in list(range(len(ts)))[::-1]:
             step = int(ts[tab_idx])
             model_t = torch.full((x.shape[0],), step, device=dev, dtype=torch.long)

@@ -8,7 +8,6 @@ the oracle (tests/test_oracle_golden.py) and, through it, the CUDA path.  Only t
 needs /root/reference; the fixtures travel with the repo.
 """
 import sys
-import typing
 from pathlib import Path
 
 import numpy as np
@@ -17,8 +16,10 @@ import torch
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "oracle" / "_shims"))
-sys.path.insert(0, "/root/reference")
-torch.Tuple = typing.Tuple  # sampler/edm_sampler.py:145 annotation no longer exists in torch 2.11
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from _ref_import import use_reference  # noqa: E402
+
+use_reference()      # `import diffbir` = the reference checkout, not this repo's alias package
 
 from diffbir_b200 import arch  # noqa: E402
 from diffbir_b200.utils.synth import make_state_dict  # noqa: E402

@@ -5,7 +5,6 @@ text config with seeded synthetic weights and token ids.
     python tests/golden/gen_golden_clip.py        ->  tests/golden/clip_small.npz
 """
 import sys
-import typing
 from pathlib import Path
 
 import numpy as np
@@ -14,8 +13,10 @@ import torch
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "oracle" / "_shims"))
-sys.path.insert(0, "/root/reference")
-torch.Tuple = typing.Tuple
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from _ref_import import use_reference  # noqa: E402
+
+use_reference()      # `import diffbir` = the reference checkout, not this repo's alias package
 
 from diffbir_b200 import arch  # noqa: E402
 from diffbir_b200.utils.synth import make_state_dict  # noqa: E402

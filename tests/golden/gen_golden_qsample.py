@@ -4,7 +4,6 @@ REFERENCE (`diffbir.model.gaussian_diffusion.Diffusion`, read-only from /root/re
     python tests/golden/gen_golden_qsample.py        ->  tests/golden/qsample.npz
 """
 import sys
-import typing
 from pathlib import Path
 
 import numpy as np
@@ -12,8 +11,10 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT / "oracle" / "_shims"))
-sys.path.insert(0, "/root/reference")
-torch.Tuple = typing.Tuple
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from _ref_import import use_reference  # noqa: E402
+
+use_reference()      # `import diffbir` = the reference checkout, not this repo's alias package
 OUT = Path(__file__).resolve().parent
 
 

@@ -5,7 +5,6 @@ from /root/reference) with an analytic stand-in for the cleaner network.
     python tests/golden/gen_golden_tiled_fn.py        ->  tests/golden/tiled_fn.npz
 """
 import sys
-import typing
 from pathlib import Path
 
 import numpy as np
@@ -14,8 +13,10 @@ import torch
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "oracle" / "_shims"))
-sys.path.insert(0, "/root/reference")
-torch.Tuple = typing.Tuple
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from _ref_import import use_reference  # noqa: E402
+
+use_reference()      # `import diffbir` = the reference checkout, not this repo's alias package
 
 OUT = Path(__file__).resolve().parent
 

@@ -93,3 +93,45 @@ def test_ownership_covers_every_tile_once():
             assert max(len(tiles_of_rank(T, r, world)) for r in range(world)) == tile_slots(T, world) >= 1
     # 49 tiles over 8 ranks: 7,6,6,6,6,6,6,6 -> 87.5 % ideal efficiency (SURVEY.md hard part 7)
     assert [len(tiles_of_rank(49, r, 8)) for r in range(8)] == [7] + [6] * 7
+
+
+# ---- batch sharding (BASELINE configs[4]: images x CFG branches over the ranks) -----------------
+def _unit_worker(rank, world, port, q, B):
+    from diffbir_b200.sampler.sampler import assemble_units
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(1)
+    nbr, C, H, W = 2, 4, 8, 8
+    x = torch.randn(B, C, H, W, generator=g)
+    c_img = torch.randn(nbr, B, C, H, W, generator=g)
+    U = nbr * B
+    mine, slots = tiles_of_rank(U, rank, world), tile_slots(U, world)
+    send = torch.zeros(slots, C, H, W)
+    for s, u in enumerate(mine):
+        j, b = divmod(u, B)
+        send[s] = _stub(x[b], 3 + j, c_img[j, b])
+    parts = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(parts, send)
+    units = assemble_units(torch.stack(parts, 0), U).view(nbr, B, C, H, W)
+    ref = torch.stack([torch.stack([_stub(x[b], 3 + j, c_img[j, b]) for b in range(B)]) for j in range(nbr)])
+    q.put((rank, bool(torch.equal(units, ref)), U, len(mine)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,B", [(2, 4), (3, 4), (3, 1)])
+def test_batch_unit_sharding_matches_single_process(world, B):
+    """(CFG branch, image) units round-robin over the ranks + padded all-gather == the un-sharded batch,
+    including U not divisible by world and U < world (ranks without a unit still join the collective)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_unit_worker, args=(r, world, port, q, B)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in results), results
+    assert sum(n for _, _, _, n in results) == 2 * B

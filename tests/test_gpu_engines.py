@@ -55,7 +55,11 @@ def test_cldm_small_vs_oracle_shapes(L, nb):
     hint = torch.randn(nb, 4, L, L, generator=gen).cuda()
     ctx = torch.randn(nb, 77, UNET_SMALL["context_dim"], generator=gen).cuda()
     scales = [1.0] * 13
+    import faulthandler
+    import os
     import time
+    if os.environ.get("DBIR_TEST_FAULTDUMP"):        # where does a slow run spend its time? (stack every N s)
+        faulthandler.dump_traceback_later(int(os.environ["DBIR_TEST_FAULTDUMP"]), repeat=True)
     t0 = time.perf_counter()
     eng.set_context(ctx)
     eng.set_timesteps([500], nb=nb)
@@ -68,6 +72,7 @@ def test_cldm_small_vs_oracle_shapes(L, nb):
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     e = rel_rms(eps, ref)
+    faulthandler.cancel_dump_traceback_later()
     print(f"cldm small L={L} nb={nb}: rel rms {e:.2e} (engine {t1 - t0:.1f}s incl. plan tuning, oracle {t2 - t1:.1f}s)")
     assert e < TOL
 

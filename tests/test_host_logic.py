@@ -42,6 +42,56 @@ def test_samplers_bit_exact_vs_reference(golden_dir):
                 np.testing.assert_array_equal(z.numpy(), ref)
 
 
+def test_edm_dpm_samplers_bit_exact_vs_reference(golden_dir):
+    """EDMSampler / DPMSolverSampler (plain-PyTorch path, analytic stand-in model) against trajectories the
+    REFERENCE produced for the same calls (tests/golden/gen_golden_samplers.py): every Karras / DPM-Solver++
+    step rule reachable from the CLI, eps and v-parameterization (zero terminal SNR), tiled and cosine-rescaled
+    CFG cases; the Brownian-tree rules with the fixture's injected noise source."""
+    import importlib.util
+    from diffbir_b200.sampler import DPMSolverSampler, EDMSampler
+    from diffbir_b200.sampler.edm import run_rule
+    spec = importlib.util.spec_from_file_location("gen_golden_samplers_cases", golden_dir / "gen_golden_samplers.py")
+    src = (golden_dir / "gen_golden_samplers.py").read_text()
+    ns = {}
+    exec(src[src.index("EDM_CASES = "):src.index("def rnd(")], ns)      # the case tables only (no reference import)
+    g = np.load(golden_dir / "samplers.npz")
+    xT = torch.from_numpy(g["xT"])
+    cond = dict(c_txt=torch.from_numpy(g["cond_c_txt"]), c_img=torch.from_numpy(g["cond_c_img"]))
+    unc = dict(c_txt=torch.from_numpy(g["uncond_c_txt"]), c_img=cond["c_img"].clone())
+
+    def stub(x, t, c):
+        tt = t.float().view(-1, 1, 1, 1) / 1000
+        return (0.3 * torch.tanh(x) + 0.05 * c["c_img"] + 0.02 * tt * x
+                + 0.01 * c["c_txt"].mean(dim=(1, 2)).view(-1, 1, 1, 1))
+
+    HP, STEPS, SHAPE = ns["HP"], ns["STEPS"], tuple(ns["SHAPE"])
+    for pname, zs in (("eps", False), ("v", True)):
+        d = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000, zero_snr=zs, parameterization=pname)
+        for solver, tiled, rc in ns["EDM_CASES"]:
+            smp = EDMSampler(d.betas, pname, rc, "edm_" + solver, **HP)
+            torch.manual_seed(7)
+            z = smp.sample(stub, "cpu", STEPS, SHAPE, cond, unc, 4.0, tiled=tiled, tile_size=16, tile_stride=8, x_T=xT.clone())
+            np.testing.assert_array_equal(z.numpy(), g[f"edm_{pname}_{solver}_{int(tiled)}_{int(rc)}"], err_msg=f"edm {pname} {solver}")
+        np.testing.assert_array_equal(smp.sigmas.numpy(), g[f"edm_sigmas_{pname}"])
+        np.testing.assert_array_equal(smp.timesteps.numpy(), g[f"edm_timesteps_{pname}"])
+        for spec_, steps, rc in ns["DPM_CASES"]:
+            nb = 1 if rc else SHAPE[0]
+            smp = DPMSolverSampler(d.betas, pname, rc, spec_)
+            z = smp.sample(stub, "cpu", steps, (nb,) + SHAPE[1:], {k: v[:nb] for k, v in cond.items()},
+                           {k: v[:nb] for k, v in unc.items()}, 4.0, x_T=xT[:nb].clone())
+            np.testing.assert_array_equal(z.numpy(), g[f"dpm_{pname}_{spec_}_{steps}_{int(rc)}"], err_msg=f"dpm {pname} {spec_}")
+        smp = EDMSampler(d.betas, pname, False, "edm_euler", **HP)
+        smp.make_schedule(STEPS)
+        den = smp.convert_to_denoiser(stub, cond, unc, 4.0)
+        x0 = xT * torch.sqrt(1.0 + smp.sigmas[0] ** 2.0)
+        for solver in ns["SDE_CASES"]:
+            gen = torch.Generator().manual_seed(11)
+            z = run_rule(solver, den, x0.clone(), smp.sigmas, HP, noise=lambda s0, s1: torch.randn(SHAPE, generator=gen))
+            np.testing.assert_array_equal(z.numpy(), g[f"sde_{pname}_{solver}"], err_msg=f"sde {pname} {solver}")
+    with pytest.raises(NotImplementedError):
+        DPMSolverSampler(d.betas, "eps", False, "dpm++_s2")
+
+
 def test_schedule_tables_and_timesteps(golden_dir):
     g = np.load(golden_dir / "sampling.npz")
     sp = SpacedSampler(g["betas_eps"], "eps", False)
@@ -205,7 +255,8 @@ def test_diffbir_alias_exposes_the_reference_names():
                        (dp, ["Pipeline", "SwinIRPipeline", "BSRNetPipeline", "SCUNetPipeline"])):
         for n in names:
             assert hasattr(mod, n), f"{mod.__name__}.{n} missing"
-    for cls in (dsm.EDMSampler, dsm.DPMSolverSampler, dp.BSRNetPipeline, dm.SCUNet, di.BIDInferenceLoop):
+    assert dsm.EDMSampler is diffbir_b200.sampler.EDMSampler and dsm.DPMSolverSampler is diffbir_b200.sampler.DPMSolverSampler
+    for cls in (dp.BSRNetPipeline, dm.SCUNet, di.BIDInferenceLoop):
         with pytest.raises(NotImplementedError):
             cls()
     # the YAML reflection targets of the reference configs resolve through the alias too

@@ -37,7 +37,7 @@ def test_cli_has_every_reference_flag_with_its_default(tmp_path):
     assert a["pos_prompt"].startswith("Cinematic") and a["neg_prompt"].startswith("painting")
 
 
-@pytest.mark.parametrize("extra,msg", [(["--sampler", "edm_dpm++_3m_sde"], "sampler"), (["--captioner", "llava"], "captioner"),
+@pytest.mark.parametrize("extra,msg", [(["--captioner", "llava"], "captioner"),
                                         (["--guidance"], "guidance"), (["--precision", "fp32"], "fp32"),
                                         (["--device", "cpu"], "CUDA"), (["--vae_decoder_tiled"], "Tiled-VAE"),
                                         (["--version", "custom"], "custom")])

@@ -59,8 +59,10 @@ def main(rep, out):
         res.append({"kernel": name, "grid": d["grid"], "us": d.get("dur", float("nan")), "tensor_pct": tensor,
                     "dram_bytes": dram, "l2_to_sm_bytes": l2sm, "l2_hit_pct": d.get("l2_hit"),
                     "regs": d.get("regs"), "smem_bytes": d.get("smem"), "warps_active_pct": d.get("occ_pct")})
+        gbs = dram / (d.get("dur", float("nan")) * 1e-6) / 1e9 if d.get("dur") else float("nan")
+        res[-1]["dram_gbs"] = gbs
         lines.append(f"{name[:44]:44s} grid {d['grid']:>16s} {d.get('dur', 0):8.1f} us  tensor-pipe {tensor:5.1f}%  "
-                     f"dram {d.get('dram_r', 0) / 1e6:7.1f}+{d.get('dram_w', 0) / 1e6:6.1f} MB ({d.get('dram_pct', 0):4.1f}% of peak)  "
+                     f"dram {d.get('dram_r', 0) / 1e6:7.1f}+{d.get('dram_w', 0) / 1e6:6.1f} MB = {gbs:6.0f} GB/s ({d.get('dram_pct', 0):4.1f}% of peak)  "
                      f"L2->SM {l2sm / 1e6:7.1f} MB  L2 hit {d.get('l2_hit', 0):4.1f}%  regs {int(d.get('regs', 0))}  "
                      f"smem {d.get('smem', 0) / 1e3:.1f} KB  warps active {d.get('occ_pct', 0):4.1f}%")
     open(out + ".json", "w").write(json.dumps(res, indent=1))

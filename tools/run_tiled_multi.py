@@ -48,6 +48,31 @@ def main():
             print(f"{name}: sharded vs single-rank: bit-equal {same}, max rel diff {rel:.2e} (rel rms {rms:.2e}); all ranks identical: {same_ranks}; "
                   f"|z| {z_multi.abs().mean():.4f}", flush=True)
         ok = ok and same and same_ranks
+    # batch sharding (BASELINE configs[4]): B images x 2 CFG branches over the ranks, one all-gather per step
+    B, Lb = 3, int(os.environ.get("DBIR_LB", "64"))
+    cond = dict(c_txt=torch.randn(B, 77, ctxd, generator=g).to(dev), c_img=torch.randn(B, 4, Lb, Lb, generator=g).to(dev))
+    unc = dict(c_txt=torch.randn(B, 77, ctxd, generator=g).to(dev), c_img=cond["c_img"].clone())
+    xT = torch.randn(B, 4, Lb, Lb, generator=g).to(dev)
+    for name, smp in (("spaced", SpacedSampler(pipe.diffusion.betas, "eps", False)),
+                      ("ddim", DDIMSampler(pipe.diffusion.betas, "eps", False, 0))):
+        smp.shard_batch = True
+        torch.manual_seed(231)
+        z_multi = smp.sample(cl, dev, steps, (B, 4, Lb, Lb), cond, unc, 4.0, x_T=xT)
+        stats = dict(smp.last_stats)
+        smp.shard_batch = False
+        cl.engine.deterministic = True        # the single-rank run with the same batch-invariant plans
+        torch.manual_seed(231)
+        z_single = smp.sample(cl, dev, steps, (B, 4, Lb, Lb), cond, unc, 4.0, x_T=xT)
+        cl.engine.deterministic = False
+        same = torch.equal(z_multi, z_single)
+        rel = ((z_multi - z_single).abs().max() / z_single.abs().max()).item()
+        allz = [torch.empty_like(z_multi) for _ in range(dist.get_world_size())]
+        dist.all_gather(allz, z_multi)
+        same_ranks = all(torch.equal(allz[0], t) for t in allz)
+        if rank == 0:
+            print(f"{name}: batch-sharded ({stats.get('forwards_per_step')} of {2 * B} forwards on rank 0) vs single-rank: "
+                  f"bit-equal {same}, max rel diff {rel:.2e}; all ranks identical: {same_ranks}", flush=True)
+        ok = ok and same and same_ranks and stats.get("batch_sharded", False)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
