@@ -348,3 +348,31 @@ def clip_text_shapes(cfg: dict) -> Shapes:
     s["ln_final.weight"] = (w,)
     s["ln_final.bias"] = (w,)
     return s
+
+
+# ------------------------------------------------------------------------------- RRDBNet (BSRNet)
+RRDBNET_CFG = dict(in_nc=3, out_nc=3, nf=64, nb=23, gc=32, sf=4)      # configs/inference/bsrnet.yaml
+
+
+def rrdbnet_shapes(cfg: dict) -> Shapes:
+    """state_dict of the reference's RRDBNet (model/bsrnet.py:36-104): conv_first, nb x RRDB of three
+    5-conv dense blocks, trunk_conv, upconv1 (+ upconv2 when sf == 4), HRconv, conv_last."""
+    nf, gc = cfg["nf"], cfg["gc"]
+    s: Shapes = OrderedDict()
+    s["conv_first.weight"] = (nf, cfg["in_nc"], 3, 3)
+    s["conv_first.bias"] = (nf,)
+    for b in range(cfg["nb"]):
+        for r in (1, 2, 3):
+            p = f"RRDB_trunk.{b}.RDB{r}."
+            for k in range(1, 5):
+                s[p + f"conv{k}.weight"] = (gc, nf + (k - 1) * gc, 3, 3)
+                s[p + f"conv{k}.bias"] = (gc,)
+            s[p + "conv5.weight"] = (nf, nf + 4 * gc, 3, 3)
+            s[p + "conv5.bias"] = (nf,)
+    names = ["trunk_conv", "upconv1"] + (["upconv2"] if cfg["sf"] == 4 else []) + ["HRconv"]
+    for nm in names:
+        s[nm + ".weight"] = (nf, nf, 3, 3)
+        s[nm + ".bias"] = (nf,)
+    s["conv_last.weight"] = (cfg["out_nc"], nf, 3, 3)
+    s["conv_last.bias"] = (cfg["out_nc"],)
+    return s

@@ -254,6 +254,35 @@ linear_f32_rows_kernel(const float* __restrict__ x, long long ldx, int m, int k,
   }
 }
 
+// y = alpha * x + z (fp32 rows of width c; z optional) -> fp32 y (optional) and a 16-bit copy with row
+// stride ld16 (the first channels of the next dense block's concat buffer). RRDBNet's block tails:
+// `out * 0.2 + x` (bsrnet.py:69-70) and the operand cast of every block output.
+__global__ void __launch_bounds__(256)
+axpby_cast_kernel(const float* __restrict__ x, float alpha, const float* __restrict__ z, long long rows, int c,
+                  float* __restrict__ y, op_t* __restrict__ y16, long long ld16) {
+  pdl_trigger();
+  pdl_wait();
+  const int V = c / 4;
+  const long long total = rows * V;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / V;
+    const int cc = static_cast<int>(i % V) * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + r * c + cc);
+    v.x = __fmul_rn(v.x, alpha); v.y = __fmul_rn(v.y, alpha); v.z = __fmul_rn(v.z, alpha); v.w = __fmul_rn(v.w, alpha);
+    if (z) {
+      const float4 t = *reinterpret_cast<const float4*>(z + r * c + cc);
+      v.x = __fadd_rn(v.x, t.x); v.y = __fadd_rn(v.y, t.y); v.z = __fadd_rn(v.z, t.z); v.w = __fadd_rn(v.w, t.w);
+    }
+    if (y) *reinterpret_cast<float4*>(y + r * c + cc) = v;
+    if (y16) {
+      uint2 o;
+      o.x = pack2(v.x, v.y); o.y = pack2(v.z, v.w);
+      *reinterpret_cast<uint2*>(y16 + r * ld16 + cc) = o;
+    }
+  }
+}
+
 // timestep_embedding(t, dim): cat(cos(t*f), sin(t*f)), f_i = exp(-ln(1e4) * i / half)
 // (util.py:128-148). out [m, dim]
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int m, int dim,
@@ -519,6 +548,15 @@ extern "C" int dbir_linear_f32(const float* x, int64_t ldx, int32_t m, int32_t k
   linear_f32_kernel<<<(n + warps_per_cta - 1) / warps_per_cta, 256, 0, ST(stream)>>>(
       x, ldx, m, k, weight, bias, n, silu_in, silu_out, y, ldy);
   DBIR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dbir_axpby_cast(const float* x, float alpha, const float* z, int64_t rows, int32_t c, float* y,
+                               void* y16, int64_t ld16, void* stream) {
+  DBIR_REQUIRE(x && (y || y16) && rows > 0 && c > 0 && c % 4 == 0, "dbir_axpby_cast: bad args");
+  DBIR_REQUIRE(!y16 || (ld16 >= c && ld16 % 4 == 0), "dbir_axpby_cast: ld16 must be >= c and a multiple of 4");
+  DBIR_CHECK_CUDA(dbir_launch(axpby_cast_kernel, dim3(grid_for(rows * (c / 4))), dim3(256), 0, ST(stream), x, alpha, z,
+                              static_cast<long long>(rows), c, y, reinterpret_cast<op_t*>(y16), static_cast<long long>(ld16)));
   return 0;
 }
 

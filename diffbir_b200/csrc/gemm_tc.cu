@@ -1026,8 +1026,12 @@ int gemm_impl(const dbir_gemm_args* a, cudaStream_t st, const TilePlan* forced) 
     p.kw = a->ksize; p.pad = a->ksize / 2;
     uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W),
                         static_cast<uint64_t>(H), static_cast<uint64_t>(NI)};
-    uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(W) * C * 2,
-                           static_cast<uint64_t>(H) * W * C * 2};
+    // lda > 0: the pixels of `a` are lda elements apart and the conv reads their first C channels (dense
+    // concat buffers: RRDBNet's cat((x, x1, ..)) lives in one [pixels, nf + 4 gc] tensor, bsrnet.py:51-56)
+    const uint64_t ps = static_cast<uint64_t>(a->lda > 0 ? a->lda : C);
+    DBIR_REQUIRE(ps >= static_cast<uint64_t>(C) && ps % 8 == 0, "dbir_gemm: conv pixel stride lda=%lld must be >= C and a multiple of 8",
+                 (long long)a->lda);
+    uint64_t strides[3] = {ps * 2, static_cast<uint64_t>(W) * ps * 2, static_cast<uint64_t>(H) * W * ps * 2};
     uint32_t box[4] = {BK, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh),
                        static_cast<uint32_t>(bni)};
     if (dbir_make_tmap(&ta, a->a, 4, dims, strides, box, 2, 1)) return -3;

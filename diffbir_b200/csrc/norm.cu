@@ -139,13 +139,14 @@ constexpr int FIN_THREADS = 256;
 // This thread's share of the (slot, channel) partial pairs of one source, four loads in flight per
 // round: the kernel is a dependent link of every GroupNorm chain and was bound by the L2 latency of
 // its one-load-at-a-time loop, not by bytes (fixed order per thread => deterministic).
-__device__ __forceinline__ void fin_accumulate(const float* __restrict__ base, int c, int lo, int w, int total,
+template <int SPLIT>
+__device__ __forceinline__ void fin_accumulate(const float* __restrict__ base, int c, int lo, int w, int total, int part,
                                                double& a, double& b) {
-  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * FIN_THREADS) {
+  for (int i0 = part * FIN_THREADS + threadIdx.x; i0 < total; i0 += 4 * SPLIT * FIN_THREADS) {
     float2 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * FIN_THREADS;
+      const int i = i0 + u * SPLIT * FIN_THREADS;
       v[u] = make_float2(0.f, 0.f);
       if (i < total) {
         const int sl = i / w, cc = lo + i % w;
@@ -157,12 +158,17 @@ __device__ __forceinline__ void fin_accumulate(const float* __restrict__ base, i
   }
 }
 
+// SPLIT > 1: a (SPLIT,1,1) cluster shares one (group, image); every CTA reduces an interleaved share of the
+// partial pairs, the shares meet in CTA 0 through distributed shared memory in rank order (deterministic).
+// A VAE layer at 512^2 has 8192 row slots x 4 channels per group: one CTA per group took 91 us there
+// (ncu: 8.4 MB read by 32 CTAs), and 16x that at 2048^2.
+template <int SPLIT>
 __global__ void __launch_bounds__(FIN_THREADS)
 gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float* __restrict__ p2,
                    int slots2, int c2, int hw, float eps, float* __restrict__ stats) {
   pdl_trigger();
   pdl_wait();
-  const int g = blockIdx.x, n = blockIdx.y;
+  const int g = blockIdx.x / SPLIT, part = blockIdx.x % SPLIT, n = blockIdx.y;
   const int C = c1 + c2, cpg = C / 32;
   const int ch0 = g * cpg, ch1 = ch0 + cpg;
   double a = 0.0, b = 0.0;
@@ -171,13 +177,13 @@ gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float
     const int lo = min(ch0, c1), hi = min(ch1, c1), w = hi - lo;
     const int total = w * slots1;
     const float* base = p1 + static_cast<long long>(n) * slots1 * c1 * 2;
-    fin_accumulate(base, c1, lo, w, total, a, b);
+    fin_accumulate<SPLIT>(base, c1, lo, w, total, part, a, b);
   }
   if (c2 > 0) {
     const int lo = max(ch0, c1) - c1, hi = max(ch1, c1) - c1, w = hi - lo;
     const int total = w * slots2;
     const float* base = p2 + static_cast<long long>(n) * slots2 * c2 * 2;
-    fin_accumulate(base, c2, lo, w, total, a, b);
+    fin_accumulate<SPLIT>(base, c2, lo, w, total, part, a, b);
   }
   // fixed-order tree: xor-shuffles inside each warp, then thread 0 adds the 8 warp sums in warp order
 #pragma unroll
@@ -186,12 +192,30 @@ gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float
     b += __shfl_xor_sync(0xffffffffu, b, o);
   }
   __shared__ double sa[FIN_THREADS / 32], sb[FIN_THREADS / 32];
+  __shared__ double s_part[2];
   if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
   __syncthreads();
+  double ta = 0.0, tb = 0.0;
   if (threadIdx.x == 0) {
-    double ta = 0.0, tb = 0.0;
 #pragma unroll
     for (int i = 0; i < FIN_THREADS / 32; ++i) { ta += sa[i]; tb += sb[i]; }
+    s_part[0] = ta; s_part[1] = tb;
+  }
+  if constexpr (SPLIT > 1) {
+    cluster_sync_all();                       // every CTA's s_part is written and visible cluster-wide
+    if (part == 0 && threadIdx.x == 0) {
+      ta = 0.0; tb = 0.0;
+      for (int r = 0; r < SPLIT; ++r) {
+        const uint32_t peer = mapa_u32(smem_u32(s_part), static_cast<uint32_t>(r));
+        double pa, pb;
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(pa) : "r"(peer) : "memory");
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(pb) : "r"(peer + 8) : "memory");
+        ta += pa; tb += pb;
+      }
+    }
+    cluster_sync_all();                       // peers stay resident until CTA 0 has read their shares
+  }
+  if (part == 0 && threadIdx.x == 0) {
     const double cnt = static_cast<double>(hw) * cpg;
     const double mean = ta / cnt;
     double var = tb / cnt - mean * mean;
@@ -230,35 +254,52 @@ gn_apply_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int 
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(hw, p_begin + pix_per_cta);
   const long long total = static_cast<long long>(p_end - p_begin) * V;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = p_begin + static_cast<int>(i / V);
-    const int c = static_cast<int>(i % V) * 4;
-    const long long pix = static_cast<long long>(n) * hw + p;
-    const float4 v = *reinterpret_cast<const float4*>(cat_ptr(s1, s2, c1, c2, pix, c));
-    float y[4] = {v.x, v.y, v.z, v.w};
-    uint2 raw;
-    raw.x = pack2(v.x, v.y); raw.y = pack2(v.z, v.w);
-    if (do_norm) {
+  // four 16-byte loads in flight per thread before the first use: at 512^2 x 128 channels (VAE) the pass
+  // streams 134 MB from HBM and the one-load-per-iteration loop reached 2.7 TB/s (ncu, 41 % of the copy peak)
+  constexpr int U = 4;
+  for (long long i0 = threadIdx.x; i0 < total; i0 += static_cast<long long>(U) * blockDim.x) {
+    float4 v[U];
+    int pp[U], cc[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) y[j] = y[j] * s_ab[2 * (c + j)] + s_ab[2 * (c + j) + 1];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + static_cast<long long>(u) * blockDim.x;
+      pp[u] = -1;
+      if (i < total) {
+        pp[u] = p_begin + static_cast<int>(i / V);
+        cc[u] = static_cast<int>(i % V) * 4;
+        v[u] = *reinterpret_cast<const float4*>(cat_ptr(s1, s2, c1, c2, static_cast<long long>(n) * hw + pp[u], cc[u]));
+      }
     }
-    if (do_silu) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
-    }
-    uint2 o;
-    o.x = pack2(y[0], y[1]); o.y = pack2(y[2], y[3]);
-    if (up == 1) {
-      *reinterpret_cast<uint2*>(out + pix * C + c) = o;
-      if (out_raw) *reinterpret_cast<uint2*>(out_raw + pix * C + c) = raw;
-    } else {
-      const int py = p / w, px = p % w;
-      const int W2 = w * 2;
-      const long long base = (static_cast<long long>(n) * (h * 2) + py * 2) * W2 + px * 2;
-      *reinterpret_cast<uint2*>(out + (base) * C + c) = o;
-      *reinterpret_cast<uint2*>(out + (base + 1) * C + c) = o;
-      *reinterpret_cast<uint2*>(out + (base + W2) * C + c) = o;
-      *reinterpret_cast<uint2*>(out + (base + W2 + 1) * C + c) = o;
+    for (int u = 0; u < U; ++u) {
+      if (pp[u] < 0) continue;
+      const int p = pp[u], c = cc[u];
+      const long long pix = static_cast<long long>(n) * hw + p;
+      float y[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      uint2 raw;
+      raw.x = pack2(v[u].x, v[u].y); raw.y = pack2(v[u].z, v[u].w);
+      if (do_norm) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = y[j] * s_ab[2 * (c + j)] + s_ab[2 * (c + j) + 1];
+      }
+      if (do_silu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
+      }
+      uint2 o;
+      o.x = pack2(y[0], y[1]); o.y = pack2(y[2], y[3]);
+      if (up == 1) {
+        *reinterpret_cast<uint2*>(out + pix * C + c) = o;
+        if (out_raw) *reinterpret_cast<uint2*>(out_raw + pix * C + c) = raw;
+      } else {
+        const int py = p / w, px = p % w;
+        const int W2 = w * 2;
+        const long long base = (static_cast<long long>(n) * (h * 2) + py * 2) * W2 + px * 2;
+        *reinterpret_cast<uint2*>(out + (base) * C + c) = o;
+        *reinterpret_cast<uint2*>(out + (base + 1) * C + c) = o;
+        *reinterpret_cast<uint2*>(out + (base + W2) * C + c) = o;
+        *reinterpret_cast<uint2*>(out + (base + W2 + 1) * C + c) = o;
+      }
     }
   }
 }
@@ -371,8 +412,20 @@ extern "C" int dbir_gn_finalize(const float* partials1, int32_t slots1, int32_t 
                                 void* stream) {
   DBIR_REQUIRE(partials1 && stats && slots1 > 0 && (c1 + c2) % 32 == 0, "dbir_gn_finalize: bad args");
   DBIR_REQUIRE(c2 == 0 || (partials2 && slots2 > 0), "dbir_gn_finalize: second source missing");
-  DBIR_CHECK_CUDA(dbir_launch(gn_finalize_kernel, dim3(32, n), dim3(FIN_THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
-                              partials1, slots1, c1, partials2, slots2, c2, hw, eps, stats));
+  // pairs per (group, image): a function of the image size and width only, never of the batch
+  const long long per_group = static_cast<long long>((c1 + c2) / 32) * (slots1 > slots2 ? slots1 : slots2);
+  const int split = per_group <= 4096 ? 1 : per_group <= 8192 ? 2 : per_group <= 16384 ? 4 : 8;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define DBIR_FIN(S)                                                                                             \
+  DBIR_CHECK_CUDA(dbir_launch_cluster(gn_finalize_kernel<S>, dim3(32 * S, n), dim3(FIN_THREADS), 0, st, S, partials1, \
+                                      slots1, c1, partials2, slots2, c2, hw, eps, stats))
+  switch (split) {
+    case 1: DBIR_FIN(1); break;
+    case 2: DBIR_FIN(2); break;
+    case 4: DBIR_FIN(4); break;
+    default: DBIR_FIN(8); break;
+  }
+#undef DBIR_FIN
   return 0;
 }
 

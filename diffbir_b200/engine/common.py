@@ -1,6 +1,8 @@
 """Shared engine plumbing: named workspace buffers and weight packing helpers."""
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Tuple
 
 import torch
@@ -107,6 +109,9 @@ def geglu_tile(c: int) -> int:
     """GEMM tile width used for the GEGLU projection of a width-c transformer block."""
     # 128-wide tiles (64 values + 64 gates): two CTAs share an SM so the erf-heavy epilogue of
     # one overlaps the mainloop of the other (measured faster than 256 on B200)
+    forced = int(os.environ.get("DBIR_GEGLU_TILE", "0"))       # A/B switch: 64 | 128 | 256
+    if forced and (8 * c) % forced == 0:
+        return forced
     return 128 if (4 * c) % 64 == 0 else 64
 
 

@@ -308,6 +308,12 @@ def linear_f32(x, ldx, m, k, weight, bias, n, y, ldy, silu_in=False, silu_out=Fa
     count_launch()
 
 
+def axpby_cast(x, alpha, z, rows, c, y=None, y16=None, ld16=0):
+    check(load().dbir_axpby_cast(_fp(x), C.c_float(alpha), _fp(z), C.c_int64(rows), c, _fp(y), _fp(y16),
+                                 C.c_int64(ld16), _sp()), "dbir_axpby_cast")
+    count_launch()
+
+
 def timestep_embedding(t, m, dim, out):
     check(load().dbir_timestep_embedding(_fp(t), m, dim, _fp(out), _sp()), "dbir_timestep_embedding")
     count_launch()

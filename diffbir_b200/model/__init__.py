@@ -1,5 +1,6 @@
+from .bsrnet import RRDBNet
 from .cldm import ControlLDM
 from .gaussian_diffusion import Diffusion
 from .swinir import SwinIR
 
-__all__ = ["ControlLDM", "Diffusion", "SwinIR"]
+__all__ = ["ControlLDM", "Diffusion", "SwinIR", "RRDBNet"]

@@ -42,7 +42,7 @@ typedef struct dbir_gemm_args {
   const float* bias;    /* [N] or NULL */
   const float* rowvec;  /* [M / rows_per_vec, N] added per row group (time embedding) or NULL */
   const float* residual;/* fp32 [rows, ldr] or NULL */
-  int64_t lda, ldb, ldo, ldr;   /* element strides; lda/ldb 0 = K */
+  int64_t lda, ldb, ldo, ldr;   /* element strides; lda/ldb 0 = K. a_mode 1: lda > 0 = pixel stride of `a` (>= img_c) */
   int32_t M, N, K;
   int32_t a_mode;       /* 0 plain matrix, 1 implicit conv (ksize x ksize, stride 1, pad ksize/2) */
   int32_t img_n, img_h, img_w, img_c, ksize;
@@ -177,6 +177,11 @@ int dbir_linear_f32(const float* x, int64_t ldx, int32_t m, int32_t k, const flo
                     const float* bias, int32_t n, int32_t silu_in, int32_t silu_out, float* y,
                     int64_t ldy, void* stream);
 int dbir_timestep_embedding(const float* t, int32_t m, int32_t dim, float* out, void* stream);
+/* y = alpha * x + z over fp32 rows [rows, c] (z may be NULL); writes fp32 y (may be NULL) and/or an op16 copy
+ * with row stride ld16 -- the tails of RRDBNet's dense blocks, `out * 0.2 + x` (bsrnet.py:69-70,85-87), and the
+ * operand cast of a block output into the next block's concat buffer. */
+int dbir_axpby_cast(const float* x, float alpha, const float* z, int64_t rows, int32_t c, float* y, void* y16,
+                    int64_t ld16, void* stream);
 int dbir_softmax_rows(const float* s, int64_t lds, int32_t rows, int32_t cols, float scale,
                       void* out, int64_t ldo, void* stream);
 int dbir_upsample2x_op16(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out,

@@ -288,14 +288,17 @@ def swinir_pipeline_run(lq_u8: np.ndarray, cleaner: Callable, encode_img: Callab
                         cleaner_tiled: bool = False, cleaner_tile_size: int = 512, cleaner_tile_stride: int = 256,
                         x_T: Optional[torch.Tensor] = None,
                         noises: Optional[List[torch.Tensor]] = None, device="cpu",
-                        set_strength: Optional[Callable] = None, taps: Optional[dict] = None):
+                        set_strength: Optional[Callable] = None, taps: Optional[dict] = None,
+                        stage1: Optional[Callable] = None, out_size: Optional[Tuple[int, int]] = None):
     """SwinIRPipeline.run (start_point 'noise', noise_aug 0, un-tiled VAE) —
     pipeline.py:235-321, 71-233, 371-397.  Callables stand for the networks:
     cleaner(img01)->img01, encode_img(img_pm1)->latent, encode_txt(list)->c_txt,
     decode(latent)->img_pm1, model(x,t,cond)->eps."""
     lq = torch.tensor(lq_u8, dtype=torch.float32, device=device).div(255).clamp(0, 1).permute(0, 3, 1, 2).contiguous()
-    out_size = tuple(lq.shape[2:])
-    clean = apply_cleaner(cleaner, lq, cleaner_tiled, cleaner_tile_size, cleaner_tile_stride)
+    # stage1 / out_size: another pipeline's apply_cleaner / set_output_size (BSRNetPipeline, pipeline.py:339-366)
+    out_size = tuple(lq.shape[2:]) if out_size is None else out_size
+    clean = (apply_cleaner(cleaner, lq, cleaner_tiled, cleaner_tile_size, cleaner_tile_stride) if stage1 is None
+             else stage1(lq))
     bs = clean.shape[0]
     cond_img = pad_to_multiple(clean, 8 if cldm_tiled else 64)
     cond = dict(c_txt=encode_txt([pos_prompt] * bs), c_img=encode_img(cond_img * 2 - 1))

@@ -7,3 +7,4 @@ CN_SMALL = dict(UNET_SMALL, hint_channels=4)
 VAE_SMALL = dict(arch.VAE_CFG, ch=64)
 SWIN_SMALL = dict(arch.SWINIR_CFG, depths=(2, 2), num_heads=(6, 6))
 CLIP_SMALL = dict(arch.CLIP_TEXT_CFG, width=128, heads=4, layers=3, vocab_size=512, embed_dim=128)
+RRDB_SMALL = dict(arch.RRDBNET_CFG, nb=2)          # same widths (the engine needs nf, nf + 4 gc multiples of 64), 2 of 23 blocks

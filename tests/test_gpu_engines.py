@@ -160,3 +160,33 @@ def test_swinir_full_config_vs_oracle(size):
     err = ((y - ref).abs().max() / ref.std()).item()
     print(f"swinir {size}: max err / std = {err:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB")
     assert err < 3e-2
+
+
+def test_rrdbnet_small_vs_reference_golden(golden_dir):
+    from diffbir_b200.engine.bsrnet import RRDBNetEngine
+    from tests.small_cfg import RRDB_SMALL
+    no_tf32()
+    g = np.load(golden_dir / "bsrnet_small.npz")
+    eng = RRDBNetEngine(make_state_dict(arch.rrdbnet_shapes(RRDB_SMALL), 7), RRDB_SMALL, "cuda")
+    y = eng.forward(torch.from_numpy(g["x"]).cuda())
+    ref = torch.from_numpy(g["y"]).cuda()
+    e = rel_rms(y, ref)
+    print(f"rrdbnet small vs reference: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB")
+    assert y.shape == ref.shape and e < TOL
+    assert torch.equal(y, eng.forward(torch.from_numpy(g["x"]).cuda()))        # graph replay: same bits
+
+
+def test_rrdbnet_full_config_vs_oracle():
+    """BSRNet (23 RRDB, configs/inference/bsrnet.yaml) on a 128x160 LQ image -> 512x640, against the fp32 oracle."""
+    from diffbir_b200.engine.bsrnet import RRDBNetEngine
+    from oracle import bsrnet as ob
+    no_tf32()
+    sd = make_state_dict(arch.rrdbnet_shapes(arch.RRDBNET_CFG), 78)
+    eng = RRDBNetEngine(sd, None, "cuda")
+    x = torch.rand(1, 3, 128, 160, generator=torch.Generator().manual_seed(4)).cuda()
+    y = eng.forward(x)
+    with torch.no_grad():
+        ref = ob.rrdbnet_forward(to_dev(sd), x)
+    e = rel_rms(y, ref)
+    print(f"rrdbnet full: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB, |y| {ref.abs().mean():.4f}")
+    assert y.shape == (1, 3, 512, 640) and e < TOL

@@ -15,7 +15,11 @@ from tests.gpu_util import no_tf32, to_dev
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_run(pipe, lq, small, seed=231, **kw):
+def _oracle_run_with(pipe, lq, kw, **extra):
+    return _oracle_run(pipe, lq, True, _extra=extra, **kw)
+
+
+def _oracle_run(pipe, lq, small, seed=231, _extra=None, **kw):
     """Oracle pipeline on the GPU in fp32 using the same state dicts the product loaded."""
     from oracle import cldm as ocl
     from oracle import sampling as osm
@@ -46,7 +50,7 @@ def _oracle_run(pipe, lq, small, seed=231, **kw):
             cldm_tile_size=kw["cldm_tile_size"], cldm_tile_stride=kw["cldm_tile_stride"], device=dev,
             cleaner_tiled=kw["cleaner_tiled"], cleaner_tile_size=kw["cleaner_tile_size"],
             cleaner_tile_stride=kw["cleaner_tile_stride"],
-            set_strength=lambda s: scales.update(s=[s] * 13), taps=taps)
+            set_strength=lambda s: scales.update(s=[s] * 13), taps=taps, **(_extra or {}))
     return out, taps
 
 
@@ -240,3 +244,31 @@ def test_edm_dpm_samplers_engine_vs_oracle_model(sampler, steps, tiled, vpred):
     e = ((z - zr).pow(2).mean().sqrt() / zr.pow(2).mean().sqrt()).item()
     print(f"{sampler} x{steps} tiled={tiled} v={vpred}: latent rel-rms {e:.2e} (|z| {zr.abs().mean():.3f})")
     assert torch.isfinite(z).all() and e < 2e-2
+
+
+def test_small_bsrnet_pipeline_matches_oracle():
+    """v2 blind-SR recipe: BSRNetPipeline (RRDBNet x4 stage 1 on the LQ image, pipeline.py:324-366) + the reduced
+    stage 2, against the oracle's restatement with the same seed."""
+    from diffbir_b200.model import RRDBNet
+    from diffbir_b200.pipeline import BSRNetPipeline
+    from oracle import bsrnet as ob
+    from tests.small_cfg import RRDB_SMALL
+    pipe0 = _pipe(True)
+    rsd = make_state_dict(arch.rrdbnet_shapes(RRDB_SMALL), 91)
+    net = RRDBNet(**RRDB_SMALL, device="cuda")
+    net.load_state_dict(rsd)
+    pipe = BSRNetPipeline(net, pipe0.cldm, pipe0.diffusion, None, "cuda", upscale=4.0)
+    pipe.taps = {}
+    lq = synthetic_lq(128, 160, seed=3)
+    kw = dict(RUN_DEFAULTS, steps=6)
+    torch.manual_seed(231)
+    out = pipe.run(lq, **kw)
+    rsd_d = to_dev(rsd)
+    pipe0.taps = pipe.taps                       # _oracle_run reads the product taps of `pipe`
+    ref, taps = _oracle_run_with(pipe0, lq, kw, stage1=lambda im: ob.bsrnet_apply_cleaner(lambda t: ob.rrdbnet_forward(rsd_d, t), im, 4.0),
+                                 out_size=(512, 640))
+    e = ((pipe.taps["z"] - taps["z"]).pow(2).mean().sqrt() / taps["z"].pow(2).mean().sqrt()).item()
+    p = _psnr_u8(out, ref)
+    print(f"small BSRNet pipeline x6: latent rel-rms {e:.2e}, uint8 PSNR {p:.1f} dB, output {out.shape}")
+    assert out.shape == ref.shape == (1, 512, 640, 3) and out.dtype == np.uint8
+    assert e < 2e-2 and p > 45.0

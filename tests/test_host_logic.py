@@ -256,7 +256,8 @@ def test_diffbir_alias_exposes_the_reference_names():
         for n in names:
             assert hasattr(mod, n), f"{mod.__name__}.{n} missing"
     assert dsm.EDMSampler is diffbir_b200.sampler.EDMSampler and dsm.DPMSolverSampler is diffbir_b200.sampler.DPMSolverSampler
-    for cls in (dp.BSRNetPipeline, dm.SCUNet, di.BIDInferenceLoop):
+    assert dm.RRDBNet is diffbir_b200.model.RRDBNet and dp.BSRNetPipeline is diffbir_b200.pipeline.BSRNetPipeline
+    for cls in (dp.SCUNetPipeline, dm.SCUNet, di.BIDInferenceLoop):
         with pytest.raises(NotImplementedError):
             cls()
     # the YAML reflection targets of the reference configs resolve through the alias too

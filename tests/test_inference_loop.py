@@ -55,6 +55,8 @@ def test_checkpoints_resolve_locally_and_fail_loudly(tmp_path):
     (tmp_path / "DiffBIR_v2.1.pt").write_bytes(b"x")
     assert resolve("v2.1", str(tmp_path)).endswith("DiffBIR_v2.1.pt")
     with pytest.raises(NotImplementedError):
+        resolve("scunet_psnr", str(tmp_path))
+    with pytest.raises(FileNotFoundError, match="BSRNet.pth"):
         resolve("bsrnet", str(tmp_path))
 
 

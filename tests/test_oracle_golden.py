@@ -159,3 +159,25 @@ def test_q_sample_matches_reference(golden_dir):
         d = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000, **kw)
         np.testing.assert_array_equal(d.q_sample(x0, t, noise).numpy(), g[f"q_{name}"])
         np.testing.assert_array_equal(osm.q_sample(osm.make_betas(zero_snr=bool(kw)), x0, t, noise).numpy(), g[f"q_{name}"])
+
+
+def test_rrdbnet_and_bsrnet_cleaner_match_reference(golden_dir):
+    """oracle.bsrnet (RRDBNet forward, BSRNetPipeline.apply_cleaner) and the product's BSRNetPipeline host code
+    (driven by the oracle network on the CPU) against a fixture the reference produced: bit-exact."""
+    from diffbir_b200.pipeline import BSRNetPipeline
+    from oracle import bsrnet as ob
+    from tests.small_cfg import RRDB_SMALL
+    g = np.load(golden_dir / "bsrnet_small.npz")
+    sd = make_state_dict(arch.rrdbnet_shapes(RRDB_SMALL), 7)
+    net = lambda im: ob.rrdbnet_forward(sd, im)               # noqa: E731
+    lq = torch.from_numpy(g["lq"])
+    with torch.no_grad():
+        np.testing.assert_array_equal(net(torch.from_numpy(g["x"])).numpy(), g["y"])
+        for scale, key in ((4.0, "cond_small"), (45.0, "cond_big")):
+            a = ob.bsrnet_apply_cleaner(net, lq, scale)
+            assert tuple(a.shape) == tuple(g[key + "_shape"])
+            np.testing.assert_array_equal(a[..., ::6, ::6].numpy(), g[key])
+            pipe = BSRNetPipeline(net, None, None, None, "cpu", upscale=scale)
+            pipe.set_output_size(lq.size())
+            b = pipe.apply_cleaner(lq, False, 512, 256)
+            np.testing.assert_array_equal(b.numpy(), a.numpy())
