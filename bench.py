@@ -224,18 +224,19 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
-def kernel_census(pipe, torch, lib):
+def kernel_census(pipe, torch, lib, nb=2, batch_invariant=None, per_shape=True):
     """Records the tensor-core launches of one ControlNet+UNet forward (batch 2 = cond/uncond of a
     512^2 image), then replays each kernel family back-to-back inside a CUDA graph and times the
     replay with CUDA events on the launching stream (steady state, same buffers as the real forward).
     Returns per-family totals and the per-shape table (per-shape numbers from per-launch events)."""
     eng = pipe.cldm.engine
     dev = eng.dev
-    eng.batch_invariant = eng.deterministic      # the plans of the 512^2 loop (the tiled run pinned the invariant ones)
-    x = torch.randn(2, 4, 64, 64, device=dev)
-    ci = torch.randn(2, 4, 64, 64, device=dev) * 0.5
-    eng.set_context(torch.randn(2, 77, 1024, device=dev))
-    eng.set_timesteps([500], 2)
+    # nb = 2: the plans of the 512^2 loop; the tiled run pins the batch-invariant ones (batch_invariant=True)
+    eng.batch_invariant = eng.deterministic if batch_invariant is None else batch_invariant
+    x = torch.randn(nb, 4, 64, 64, device=dev)
+    ci = torch.randn(nb, 4, 64, 64, device=dev) * 0.5
+    eng.set_context(torch.randn(nb, 77, 1024, device=dev))
+    eng.set_timesteps([500], nb)
     eng.load_step(0)
     two = eng.two_streams
     eng.two_streams = False                  # record on one stream
@@ -274,8 +275,9 @@ def kernel_census(pipe, torch, lib):
     by_shape = {}
     for c in calls:
         by_shape.setdefault((c[0],) + tuple(c[1]), []).append(c)
-    for k, sel in by_shape.items():      # per-shape: the launches of that shape back-to-back in a graph
-        shapes[k] = [sum(c[2] for c in sel), replay_ms(sel, 3), len(sel)]
+    if per_shape:
+        for k, sel in by_shape.items():      # per-shape: the launches of that shape back-to-back in a graph
+            shapes[k] = [sum(c[2] for c in sel), replay_ms(sel, 3), len(sel)]
     return fam, shapes
 
 
@@ -559,6 +561,15 @@ def run_ours(args):
             "attention": {"achieved": att[0] / (att[1] * 1e-3) / 1e12, "frac": att[0] / (att[1] * 1e-3) / 1e12 / peak_tf,
                           "ms_per_forward": att[1]},
             "tensor_kernel_ms_per_forward": forward_ms}
+    if not args.no_tiled:
+        # the same family in the regime of the sharded tiled run: 14 tile-forwards per replay = the per-rank batch
+        # of 49 tiles x 2 CFG branches on 8 GPUs, batch-invariant plans (no split-K)
+        tfam, _ = kernel_census(pipe, torch, lib, nb=14, batch_invariant=True, per_shape=False)
+        tg, ta = tfam[gname], tfam.get("attention (attn_fwd_kernel)", [0, 1, 0])
+        roof["tiled_regime"] = {
+            "forwards_per_replay": 14, "gemm_tflops": tg[0] / (tg[1] * 1e-3) / 1e12, "gemm_frac": tg[0] / (tg[1] * 1e-3) / 1e12 / peak_tf,
+            "gemm_ms": tg[1], "attention_tflops": ta[0] / (ta[1] * 1e-3) / 1e12, "attention_frac": ta[0] / (ta[1] * 1e-3) / 1e12 / peak_tf,
+            "attention_ms": ta[1], "note": "same kernel families at the per-rank batch of the 8-GPU tiled-2048 run (batch-invariant plans)"}
     prof_dir = ROOT / "gpurun_out"
     prof_dir.mkdir(exist_ok=True)
     with open(prof_dir / "kernel_census.csv", "w") as f:
