@@ -465,7 +465,9 @@ namespace {
 long long* g_attn_dbg = nullptr;
 }
 /* calibration only: per-CTA clock64 sums of the next attention launches go to `buf` ([ctas][8] int64), NULL = off */
+#ifdef DBIR_DEBUG_PROBES
 extern "C" void dbir_debug_attn_stamps(void* buf) { g_attn_dbg = reinterpret_cast<long long*>(buf); }
+#endif
 
 namespace {
 // Stream-K decomposition: used when whole tiles would leave the last wave of CTA slots (two per SM)

@@ -1,5 +1,8 @@
 // Micro-probes used to calibrate the kernels' cost models (not part of the product path):
 // tcgen05.mma issue-to-retire rate for a given tile shape / operand layout.
+// Compiled only into probe builds: python -m diffbir_b200.build --tag=probes -DDBIR_DEBUG_PROBES
+// (loaded with DBIR_LIB_TAG=probes); the product libraries carry no calibration code.
+#ifdef DBIR_DEBUG_PROBES
 #include "common.cuh"
 #include "../../include/diffbir_b200.h"
 
@@ -75,3 +78,5 @@ extern "C" int dbir_debug_mma_rate(int32_t n, int32_t b_mn_major, int32_t iters,
   DBIR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+#endif  // DBIR_DEBUG_PROBES

@@ -162,27 +162,6 @@ __device__ __forceinline__ void fin_accumulate(const float* __restrict__ base, i
 // partial pairs, the shares meet in CTA 0 through distributed shared memory in rank order (deterministic).
 // A VAE layer at 512^2 has 8192 row slots x 4 channels per group: one CTA per group took 91 us there
 // (ncu: 8.4 MB read by 32 CTAs), and 16x that at 2048^2.
-// Sum / sum of squares of group g of image n over this CTA's share (`part` of SPLIT) of the partial pairs of
-// the virtual concat; identical code (and bits) in the stand-alone finalize kernel and in the fused apply.
-template <int SPLIT>
-__device__ __forceinline__ void fin_group_sums(const float* __restrict__ p1, int slots1, int c1,
-                                               const float* __restrict__ p2, int slots2, int c2, int g, int n, int part,
-                                               double& a, double& b) {
-  const int C = c1 + c2, cpg = C / 32;
-  const int ch0 = g * cpg, ch1 = ch0 + cpg;
-  a = 0.0; b = 0.0;
-  {   // source 1: channels [ch0, ch1) ∩ [0, c1)
-    const int lo = min(ch0, c1), hi = min(ch1, c1), w = hi - lo;
-    const float* base = p1 + static_cast<long long>(n) * slots1 * c1 * 2;
-    fin_accumulate<SPLIT>(base, c1, lo, w, w * slots1, part, a, b);
-  }
-  if (c2 > 0) {
-    const int lo = max(ch0, c1) - c1, hi = max(ch1, c1) - c1, w = hi - lo;
-    const float* base = p2 + static_cast<long long>(n) * slots2 * c2 * 2;
-    fin_accumulate<SPLIT>(base, c2, lo, w, w * slots2, part, a, b);
-  }
-}
-
 template <int SPLIT>
 __global__ void __launch_bounds__(FIN_THREADS)
 gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float* __restrict__ p2,
@@ -191,8 +170,21 @@ gn_finalize_kernel(const float* __restrict__ p1, int slots1, int c1, const float
   pdl_wait();
   const int g = blockIdx.x / SPLIT, part = blockIdx.x % SPLIT, n = blockIdx.y;
   const int C = c1 + c2, cpg = C / 32;
-  double a, b;
-  fin_group_sums<SPLIT>(p1, slots1, c1, p2, slots2, c2, g, n, part, a, b);
+  const int ch0 = g * cpg, ch1 = ch0 + cpg;
+  double a = 0.0, b = 0.0;
+  // source 1: channels [ch0, ch1) ∩ [0, c1)
+  {
+    const int lo = min(ch0, c1), hi = min(ch1, c1), w = hi - lo;
+    const int total = w * slots1;
+    const float* base = p1 + static_cast<long long>(n) * slots1 * c1 * 2;
+    fin_accumulate<SPLIT>(base, c1, lo, w, total, part, a, b);
+  }
+  if (c2 > 0) {
+    const int lo = max(ch0, c1) - c1, hi = max(ch1, c1) - c1, w = hi - lo;
+    const int total = w * slots2;
+    const float* base = p2 + static_cast<long long>(n) * slots2 * c2 * 2;
+    fin_accumulate<SPLIT>(base, c2, lo, w, total, part, a, b);
+  }
   // fixed-order tree: xor-shuffles inside each warp, then thread 0 adds the 8 warp sums in warp order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -239,78 +231,24 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int c1, int c2,
                 int h, int w, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int do_norm, int do_silu, int up,
-                op_t* __restrict__ out, op_t* __restrict__ out_raw, int pix_per_cta, int imgs_per_group,
-                const float* __restrict__ p1, int slots1, const float* __restrict__ p2, int slots2, float eps,
-                float* __restrict__ stats_w, unsigned int* __restrict__ sync) {
+                op_t* __restrict__ out, op_t* __restrict__ out_raw, int pix_per_cta, int imgs_per_group) {
   extern __shared__ float s_ab[];   // [C][2]
   pdl_trigger();
   pdl_wait();
   const int C = c1 + c2;
   const int n = blockIdx.y;
   const int hw = h * w;
-  if (p1) {
-    // Fused statistics finalisation (was a separate dbir_gn_finalize launch in front of every GroupNorm):
-    // CTAs 0..31 of image n first reduce one group each from the producer's partial sums (same code and
-    // bits as gn_finalize_kernel<1>), publish mean / rstd and count themselves on sync[2n]; every CTA
-    // of the image then waits for the 32 groups. Waiters only ever wait for CTAs with LOWER block
-    // indices of the same launch (dispatched first), so the wait cannot dead-lock; it is bounded and
-    // traps instead of hanging. The last CTA through resets the counters for the next launch.
-    __shared__ double f_sa[FIN_THREADS / 32], f_sb[FIN_THREADS / 32];
-    const int cpg = C / 32;
-    unsigned int mine = 0;
-    for (int g = blockIdx.x; g < 32; g += gridDim.x) {
-      double a, b;
-      fin_group_sums<1>(p1, slots1, c1, p2, slots2, c2, g, n, 0, a, b);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-      }
-      if ((threadIdx.x & 31) == 0) { f_sa[threadIdx.x >> 5] = a; f_sb[threadIdx.x >> 5] = b; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double ta = 0.0, tb = 0.0;
-#pragma unroll
-        for (int i = 0; i < FIN_THREADS / 32; ++i) { ta += f_sa[i]; tb += f_sb[i]; }
-        const double cnt = static_cast<double>(hw) * cpg;
-        const double mean = ta / cnt;
-        double var = tb / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        __stcg(stats_w + (n * 32 + g) * 2 + 0, static_cast<float>(mean));
-        __stcg(stats_w + (n * 32 + g) * 2 + 1, static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
-      }
-      __syncthreads();
-      ++mine;
-    }
-    if (threadIdx.x == 0) {
-      if (mine) { __threadfence(); atomicAdd(&sync[2 * n], mine); }
-      unsigned int seen = 0;
-      long long t0 = 0;
-      while (true) {
-        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(sync + 2 * n) : "memory");
-        if (seen >= 32u) break;
-        if (t0 == 0) t0 = clock64();
-        else if (clock64() - t0 > 4000000000LL) { printf("dbir: gn_apply statistics wait timed out (image %d)\n", n); __trap(); }
-      }
-    }
-    __syncthreads();
-  }
   if (do_norm) {
     const int cpg = C / 32;
     const int goff = imgs_per_group > 0 ? (n / imgs_per_group) * C : 0;     // stacked twin problems
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g = c / cpg;
-      // L2 reads: in the fused mode the values were just written by other SMs of this very launch
-      const float mean = __ldcg(stats + (n * 32 + g) * 2), rstd = __ldcg(stats + (n * 32 + g) * 2 + 1);
+      const float mean = stats[(n * 32 + g) * 2], rstd = stats[(n * 32 + g) * 2 + 1];
       const float a = gamma[goff + c] * rstd;
       s_ab[2 * c] = a;
       s_ab[2 * c + 1] = beta[goff + c] - mean * a;
     }
     __syncthreads();
-  }
-  if (p1 && threadIdx.x == 0) {             // every CTA of the image has its statistics: the last one re-arms
-    const unsigned int t = atomicAdd(&sync[2 * n + 1], 1u);
-    if (t == gridDim.x - 1) { sync[2 * n] = 0u; sync[2 * n + 1] = 0u; }
   }
   const int V = C / 4;
   const int p_begin = blockIdx.x * pix_per_cta;
@@ -491,17 +429,17 @@ extern "C" int dbir_gn_finalize(const float* partials1, int32_t slots1, int32_t 
   return 0;
 }
 
-static int gn_apply_impl(const float* src1, const float* src2, int32_t c1, int32_t c2, int32_t n, int32_t h,
-                         int32_t w, const float* stats, const float* gamma, const float* beta, int32_t do_norm,
-                         int32_t do_silu, int32_t upsample, void* out, void* out_raw, int32_t imgs_per_group,
-                         const float* p1, int32_t slots1, const float* p2, int32_t slots2, float eps, float* stats_w,
-                         unsigned int* sync, void* stream, const char* who) {
+extern "C" int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, int32_t c2,
+                             int32_t n, int32_t h, int32_t w, const float* stats,
+                             const float* gamma, const float* beta, int32_t do_norm,
+                             int32_t do_silu, int32_t upsample, void* out, void* out_raw,
+                             int32_t imgs_per_group, void* stream) {
   const int C = c1 + c2;
-  DBIR_REQUIRE(src1 && out, "%s: null pointer", who);
-  DBIR_REQUIRE(c1 % 4 == 0 && c2 % 4 == 0, "%s: channels must be multiples of 4", who);
-  DBIR_REQUIRE(!do_norm || (stats && gamma && beta && C % 32 == 0), "%s: norm args", who);
-  DBIR_REQUIRE(upsample == 1 || upsample == 2, "%s: upsample must be 1 or 2", who);
-  DBIR_REQUIRE(!(upsample == 2 && out_raw), "%s: raw copy unsupported with upsample", who);
+  DBIR_REQUIRE(src1 && out, "dbir_gn_apply: null pointer");
+  DBIR_REQUIRE(c1 % 4 == 0 && c2 % 4 == 0, "dbir_gn_apply: channels must be multiples of 4");
+  DBIR_REQUIRE(!do_norm || (stats && gamma && beta && C % 32 == 0), "dbir_gn_apply: norm args");
+  DBIR_REQUIRE(upsample == 1 || upsample == 2, "dbir_gn_apply: upsample must be 1 or 2");
+  DBIR_REQUIRE(!(upsample == 2 && out_raw), "dbir_gn_apply: raw copy unsupported with upsample");
   const int hw = h * w;
   const int target = 4 * dbir_sm_count();
   int ctas = (target + n - 1) / n;
@@ -511,39 +449,8 @@ static int gn_apply_impl(const float* src1, const float* src2, int32_t c1, int32
   const size_t smem = do_norm ? static_cast<size_t>(C) * 2 * sizeof(float) : 0;
   DBIR_CHECK_CUDA(dbir_launch(gn_apply_kernel, dim3(ctas, n), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream),
                               src1, src2, c1, c2, h, w, stats, gamma, beta, do_norm, do_silu, upsample,
-                              reinterpret_cast<op_t*>(out), reinterpret_cast<op_t*>(out_raw), ppc, imgs_per_group, p1,
-                              slots1, p2, slots2, eps, stats_w, sync));
+                              reinterpret_cast<op_t*>(out), reinterpret_cast<op_t*>(out_raw), ppc, imgs_per_group));
   return 0;
-}
-
-extern "C" int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, int32_t c2,
-                             int32_t n, int32_t h, int32_t w, const float* stats,
-                             const float* gamma, const float* beta, int32_t do_norm,
-                             int32_t do_silu, int32_t upsample, void* out, void* out_raw,
-                             int32_t imgs_per_group, void* stream) {
-  return gn_apply_impl(src1, src2, c1, c2, n, h, w, stats, gamma, beta, do_norm, do_silu, upsample, out, out_raw,
-                       imgs_per_group, nullptr, 0, nullptr, 0, 0.f, nullptr, nullptr, stream, "dbir_gn_apply");
-}
-
-/* 1 when dbir_gn_apply_fused can take these partial sums (few enough pairs per group for one CTA to fold
- * them in a microsecond or two); larger images keep the stand-alone, cluster-split dbir_gn_finalize. */
-extern "C" int32_t dbir_gn_fused_ok(int32_t slots1, int32_t slots2, int32_t c) {
-  const long long per_group = static_cast<long long>(c / 32) * (slots1 > slots2 ? slots1 : slots2);
-  return per_group <= 4096 ? 1 : 0;
-}
-
-extern "C" int dbir_gn_apply_fused(const float* src1, const float* src2, int32_t c1, int32_t c2, int32_t n, int32_t h,
-                                   int32_t w, const float* partials1, int32_t slots1, const float* partials2,
-                                   int32_t slots2, float eps, float* stats, void* sync, const float* gamma,
-                                   const float* beta, int32_t do_silu, int32_t upsample, void* out, void* out_raw,
-                                   int32_t imgs_per_group, void* stream) {
-  DBIR_REQUIRE(partials1 && slots1 > 0 && stats && sync, "dbir_gn_apply_fused: null pointer");
-  DBIR_REQUIRE(c2 == 0 || (partials2 && slots2 > 0), "dbir_gn_apply_fused: second source missing");
-  DBIR_REQUIRE(dbir_gn_fused_ok(slots1, slots2, c1 + c2), "dbir_gn_apply_fused: too many partial sums per group; "
-               "use dbir_gn_finalize + dbir_gn_apply");
-  return gn_apply_impl(src1, src2, c1, c2, n, h, w, stats, gamma, beta, 1, do_silu, upsample, out, out_raw,
-                       imgs_per_group, partials1, slots1, partials2, slots2, eps, stats,
-                       reinterpret_cast<unsigned int*>(sync), stream, "dbir_gn_apply_fused");
 }
 
 extern "C" int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t c,

@@ -170,7 +170,6 @@ class CldmEngine:
         self._wseq, self._wpos = {}, {}  # per-stream weight sequence of the forward (L2 prefetch lookahead)
         self.prefetch_weights = False    # measured: no gain on B200 (7.53 vs 7.45 ms per forward), kept opt-in
         self.fuse_gn_stats = True
-        self.fuse_gn_finalize = os.environ.get("DBIR_GN_FUSED", "1") != "0"     # dbir_gn_apply_fused (A/B switch)
         # Batch-invariant kernel plans: no split-K, whole attention tiles per CTA. Every sample's result
         # then has the same bits whatever batch it runs in (tiled sampling: sharded == single rank) and
         # whatever plan the timing-based tuner picked (run-to-run / process-to-process reproducible).
@@ -302,13 +301,6 @@ class CldmEngine:
         p1 = self._part.get(src1.data_ptr())
         p2 = self._part.get(src2.data_ptr()) if src2 is not None else None
         if self.fuse_gn_stats and p1 is not None and (src2 is None or p2 is not None):
-            if self.fuse_gn_finalize and lib.gn_fused_ok(p1[1], p2[1] if p2 else 0, c1 + c2):
-                # statistics finalisation inside the apply kernel: one launch per GroupNorm instead of two
-                sync = ws.get(tag + ":gn_sync", (2 * nb,), torch.int32, zero=True)
-                lib.gn_apply_fused(src1, src2, c1, c2, nb, h, w, p1[0], p1[1], p2[0] if p2 else None, p2[1] if p2 else 0,
-                                   eps, stats, sync, gamma, beta, out16, silu=silu, out_raw=out_raw,
-                                   imgs_per_group=nb // G if G > 1 else 0)
-                return
             lib.gn_finalize(p1[0], p1[1], c1, p2[0] if p2 else None, p2[1] if p2 else 0, c2, nb, h * w, eps, stats)
         else:
             wsp = ws.get(tag + ":gn_ws", (lib.gn_workspace_floats(nb, h * w, c1 + c2),), torch.float32, zero=True)

@@ -68,11 +68,6 @@ class VaeEngine:
         stats = ws.get("gn_stats", (nb * 64,), torch.float32)
         part = self._part.get(x.data_ptr())
         if part is not None:
-            if lib.gn_fused_ok(part[1], 0, c):       # small images: finalisation inside the apply kernel
-                sync = ws.get("gn_sync", (2 * nb,), torch.int32, zero=True)
-                lib.gn_apply_fused(x, None, c, 0, nb, h, w, part[0], part[1], None, 0, 1e-6, stats, sync, gamma, beta,
-                                   out16, silu=silu, out_raw=out_raw)
-                return
             lib.gn_finalize(part[0], part[1], c, None, 0, 0, nb, h * w, 1e-6, stats)
         else:
             wsp = ws.get("gn_ws", (lib.gn_workspace_floats(nb, h * w, c),), torch.float32, zero=True)

@@ -266,18 +266,6 @@ def gn_apply(src1, src2, c1, c2, n, h, w, stats, gamma, beta, out, *, norm=True,
     count_launch()
 
 
-def gn_fused_ok(slots1, slots2, c) -> bool:
-    return bool(load().dbir_gn_fused_ok(slots1, slots2, c))
-
-
-def gn_apply_fused(src1, src2, c1, c2, n, h, w, p1, slots1, p2, slots2, eps, stats, sync, gamma, beta, out, *,
-                   silu=True, upsample=1, out_raw=None, imgs_per_group=0):
-    check(load().dbir_gn_apply_fused(_fp(src1), _fp(src2), c1, c2, n, h, w, _fp(p1), slots1, _fp(p2), slots2,
-                                     C.c_float(eps), _fp(stats), _fp(sync), _fp(gamma), _fp(beta), 1 if silu else 0,
-                                     upsample, _fp(out), _fp(out_raw), imgs_per_group, _sp()), "dbir_gn_apply_fused")
-    count_launch()
-
-
 def layernorm(x, ldx, rows, c, gamma, beta, out, ldo, eps=1e-5, rows_per_group=0):
     check(load().dbir_layernorm(_fp(x), C.c_int64(ldx), rows, c, _fp(gamma), _fp(beta),
                                 C.c_float(eps), _fp(out), C.c_int64(ldo),

@@ -130,16 +130,6 @@ int dbir_gn_apply(const float* src1, const float* src2, int32_t c1, int32_t c2, 
                   int32_t h, int32_t w, const float* stats, const float* gamma,
                   const float* beta, int32_t do_norm, int32_t do_silu, int32_t upsample,
                   void* out, void* out_raw, int32_t imgs_per_group, void* stream);
-/* dbir_gn_finalize + dbir_gn_apply(do_norm = 1) as ONE launch: the first 32 CTAs of each image fold the partial
- * sums (same arithmetic and bits as dbir_gn_finalize), the rest wait for them inside the kernel. `stats`
- * [n][32][2] receives mean / rstd; `sync` = 2 * n uint32, zero-initialised ONCE by the caller and private to
- * one stream (the kernel re-arms it). Only when dbir_gn_fused_ok(slots1, slots2, c1 + c2) is 1. */
-int32_t dbir_gn_fused_ok(int32_t slots1, int32_t slots2, int32_t c);
-int dbir_gn_apply_fused(const float* src1, const float* src2, int32_t c1, int32_t c2, int32_t n, int32_t h,
-                        int32_t w, const float* partials1, int32_t slots1, const float* partials2, int32_t slots2,
-                        float eps, float* stats, void* sync, const float* gamma, const float* beta,
-                        int32_t do_silu, int32_t upsample, void* out, void* out_raw, int32_t imgs_per_group,
-                        void* stream);
 int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t c, const float* gamma,
                    const float* beta, float eps, void* out, int64_t ldo, int32_t out_kind,
                    int32_t rows_per_group, void* stream);   /* out_kind 0 = fp32, 1 = op16 */
@@ -210,11 +200,15 @@ int dbir_tile_blend(const float* tiles, int32_t b, int32_t c, int32_t h, int32_t
                     const int32_t* coords, int32_t ntiles, int32_t tile, const float* weights,
                     float* out, void* stream);
 
-/* ---- calibration probe (not part of the product path) ------------------------------------
+/* ---- calibration probes: only in builds made with -DDBIR_DEBUG_PROBES (python -m diffbir_b200.build
+ * --tag=probes -DDBIR_DEBUG_PROBES -DDBIR_ATTN_PROBE, loaded with DBIR_LIB_TAG=probes); the product libraries
+ * do not export them.
  * Cycles for `iters` back-to-back 128 x n x 16 tcgen05 MMAs (one CTA) into out_cycles[0] (int64). */
+#ifdef DBIR_DEBUG_PROBES
 void dbir_debug_attn_stamps(void* buf);   /* per-CTA clock64 sums of later attention launches -> buf [ctas][8] int64; NULL = off */
 int dbir_debug_mma_rate(int32_t n, int32_t b_mn_major, int32_t iters, int32_t a_in_tmem, void* out_cycles,
                         void* stream);
+#endif
 
 /* ---- fused output epilogue -------------------------------------------------------------
  * fixed = high_freq((sample + 1) / 2) + low_freq(style): wavelet_reconstruction (utils/common.py:29-77,

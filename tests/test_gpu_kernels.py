@@ -395,21 +395,6 @@ def test_fused_groupnorm_statistics(L, n, h, w, c1, c2):
     st = stats.view(n, 32, 2)
     assert (st[..., 0].double() - mean).abs().max() < 1e-4 * (mean.abs().max() + 1)
     assert ((st[..., 1].double() - 1 / (var + 1e-5).sqrt()).abs() / (1 / (var + 1e-5).sqrt())).max() < 1e-4
-    # one-launch variant (finalisation inside the apply kernel): same statistics bits, same output bits,
-    # repeated launches re-arm their counters
-    assert L.gn_fused_ok(parts[0][1], parts[1][1], c)
-    gamma, beta = rnd(c, seed=40) * 0.2 + 1.0, rnd(c, seed=41) * 0.1
-    ref16 = torch.empty(n * hw, c, dtype=dt, device="cuda")
-    L.gn_apply(outs[0], outs[1], c1, c2, n, h, w, stats, gamma, beta, ref16, norm=True, silu=True)
-    sync = torch.zeros(2 * n, dtype=torch.int32, device="cuda")
-    for _ in range(3):
-        stats2 = torch.full((n * 64,), float("nan"), device="cuda")
-        got16 = torch.zeros(n * hw, c, dtype=dt, device="cuda")
-        L.gn_apply_fused(outs[0], outs[1], c1, c2, n, h, w, parts[0][0], parts[0][1], parts[1][0], parts[1][1], 1e-5,
-                         stats2, sync, gamma, beta, got16, silu=True)
-        torch.cuda.synchronize()
-        assert torch.equal(stats2, stats) and torch.equal(got16, ref16)
-        assert (sync == 0).all()
 
 
 @pytest.mark.parametrize("b,h,w,shift", [(1, 64, 64, 0), (1, 64, 64, 4), (2, 16, 24, 4), (1, 128, 64, 4)])

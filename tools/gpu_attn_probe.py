@@ -1,4 +1,6 @@
-"""Where an attention CTA's time goes (clock64 sums per CTA: softmax-warp waits vs work, MMA-warp waits)."""
+"""(needs the probe build: python -m diffbir_b200.build --tag=probes -DDBIR_DEBUG_PROBES -DDBIR_ATTN_PROBE;
+run with DBIR_LIB_TAG=probes)
+Where an attention CTA's time goes (clock64 sums per CTA: softmax-warp waits vs work, MMA-warp waits)."""
 import ctypes as C
 import os
 import sys

@@ -1,4 +1,6 @@
-"""tcgen05.mma retire rate by tile shape / operand layout (calibrates the GEMM / attention models)."""
+"""(needs the probe build: python -m diffbir_b200.build --tag=probes -DDBIR_DEBUG_PROBES -DDBIR_ATTN_PROBE;
+run with DBIR_LIB_TAG=probes)
+tcgen05.mma retire rate by tile shape / operand layout (calibrates the GEMM / attention models)."""
 import ctypes as C
 import sys
 from pathlib import Path
