@@ -461,7 +461,7 @@ def run_ours(args):
             [sum(t_ms), sum(t_e2e_ms), (sum(ag) / len(ag)) if ag else 0.0, tphases.get("sampler_loop", 0.0),
              sum(v for k, v in tphases.items() if k != "sampler_loop")])
         counts = torch.zeros(world, device=dev, dtype=torch.float64)
-        counts[rank] = stats.get("tiles_this_rank", 0)
+        counts[rank] = stats.get("units_this_rank", 0)
         if world > 1:
             dist.all_reduce(counts)
         mp = args.tiled_images * 2048 * 2048 / 1e6
@@ -469,14 +469,15 @@ def run_ours(args):
                  "ms_per_image": t_total / args.tiled_images,
                  "e2e": {"value": mp / (t_e2e_total / 1e3), "unit": "MPix/s", "h2d_bytes_per_step": int(lq_t.nbytes),
                          "d2h_bytes_per_step": int(out_t.nbytes)},
-                 "tiles": int(stats.get("tiles", 0)), "tiles_per_rank": [int(c) for c in counts.tolist()],
-                 "tile_forwards_per_step_max_rank": int(2 * max(counts.tolist())),
+                 "tiles": int(stats.get("tiles", 0)), "tile_forwards_per_rank": [int(c) for c in counts.tolist()],
+                 "tile_forwards_per_step_max_rank": int(max(counts.tolist())),
                  "allgather_ms_per_step": ag_mean, "allgather_bytes_per_rank_per_step":
-                     int(2 * ((stats.get("tiles", 0) + world - 1) // world) * 4 * 64 * 64 * 4) if world > 1 else 0,
+                     int(((2 * stats.get("tiles", 0) + world - 1) // world) * 4 * 64 * 64 * 4) if world > 1 else 0,
                  "sampler_loop_ms": loop_ms, "replicated_serial_ms": serial_ms,
                  "phases_ms_rank0": tphases,
-                 "workload": "Tiled BSR 2048x2048, tile 512 stride 256: 49 latent tiles sharded round-robin over the ranks, "
-                             "one NCCL all-gather of per-tile eps per step (configs[3]); SwinIR / VAE / CLIP replicated"}
+                 "workload": "Tiled BSR 2048x2048, tile 512 stride 256: the 98 (latent tile, CFG branch) forwards of a step sharded "
+                             "round-robin over the ranks, one NCCL all-gather of per-tile eps per step (configs[3]); SwinIR / VAE / "
+                             "CLIP replicated"}
 
     # ------------------------------------------------------------------ v2.1 1024^2 batch 4 (configs[4])
     v21 = None

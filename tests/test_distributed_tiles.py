@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from diffbir_b200.sampler.sampler import assemble_gathered, tile_slots, tiles_of_rank
+from diffbir_b200.sampler.sampler import assemble_units, tile_slots, tiles_of_rank
 from diffbir_b200.utils.common import gaussian_weights, sliding_windows
 
 
@@ -28,30 +28,35 @@ def _reference_tiled(x, c_img, t, size, stride):
 
 
 def _worker(rank, world, port, q, H=24, W=40):
+    """Mirrors EngineEval's tiled sharding: unit u = branch * T + tile, owner u % world, padded all-gather,
+    assemble_units, per-branch blend in the reference's row-major accumulation order."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = torch.Generator().manual_seed(0)               # same data on every rank
-    size, stride, B, C = 16, 8, 1, 4
-    x, c_img = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    size, stride, B, C, nbr = 16, 8, 1, 4, 2
+    x = torch.randn(B, C, H, W, generator=g)
+    c_imgs = [torch.randn(B, C, H, W, generator=g) for _ in range(nbr)]
     wins = sliding_windows(H, W, size, stride)
     T = len(wins)
-    mine, slots = tiles_of_rank(T, rank, world), tile_slots(T, world)
-    send = torch.zeros(1, slots, B, C, size, size)
-    for s, t in enumerate(mine):
+    U = nbr * T
+    mine, slots = tiles_of_rank(U, rank, world), tile_slots(U, world)
+    send = torch.zeros(slots, B, C, size, size)
+    for s, u in enumerate(mine):
+        j, t = divmod(u, T)
         a, b, c, d = wins[t]
-        send[0, s] = _stub(x[..., a:b, c:d], 7, c_img[..., a:b, c:d])
+        send[s] = _stub(x[..., a:b, c:d], 7 + j, c_imgs[j][..., a:b, c:d])
     parts = [torch.empty_like(send) for _ in range(world)]
     dist.all_gather(parts, send)                        # gloo: list form (NCCL path uses _into_tensor)
-    recv = torch.stack(parts, 0)
-    tiles = assemble_gathered(recv)[0]                 # [slots*world, B, C, size, size]
-    out, cnt = torch.zeros_like(x), torch.zeros_like(x)
+    tiles = assemble_units(torch.stack(parts, 0), U).view(nbr, T, B, C, size, size)
     w = torch.tensor(gaussian_weights(size, size)[None, None], dtype=x.dtype)
-    for t, (a, b, c, d) in enumerate(wins):            # reference accumulation order
-        out[..., a:b, c:d] += tiles[t] * w
-        cnt[..., a:b, c:d] += w
-    res = out / cnt
-    ref = _reference_tiled(x, c_img, 7, size, stride)
-    q.put((rank, bool(torch.equal(res, ref)), T, len(mine)))
+    ok = True
+    for j in range(nbr):
+        out, cnt = torch.zeros_like(x), torch.zeros_like(x)
+        for t, (a, b, c, d) in enumerate(wins):        # reference accumulation order
+            out[..., a:b, c:d] += tiles[j, t] * w
+            cnt[..., a:b, c:d] += w
+        ok = ok and bool(torch.equal(out / cnt, _reference_tiled(x, c_imgs[j], 7 + j, size, stride)))
+    q.put((rank, ok, T, len(mine)))
     dist.destroy_process_group()
 
 
@@ -74,15 +79,15 @@ def _run_world(world, H, W):
 def test_two_rank_tile_sharding_matches_single_process():
     results = _run_world(2, 24, 40)
     counts = sorted(n for _, _, _, n in results)
-    assert sum(counts) == results[0][2] and counts[1] - counts[0] <= 1
+    assert sum(counts) == 2 * results[0][2] and counts[1] - counts[0] <= 1
 
 
 def test_fewer_tiles_than_ranks():
     """T < world (e.g. a 768^2 image on 8 GPUs): ranks without a tile send a zero buffer, still join
     the all-gather, and every rank blends the same result (used to dead-lock)."""
-    results = _run_world(3, 16, 24)                    # 2 tiles on 3 ranks
+    results = _run_world(5, 16, 24)                    # 2 tiles x 2 branches = 4 units on 5 ranks
     assert results[0][2] == 2
-    assert sorted(n for _, _, _, n in results) == [0, 1, 1]
+    assert sorted(n for _, _, _, n in results) == [0, 1, 1, 1, 1]
 
 
 def test_ownership_covers_every_tile_once():
@@ -91,13 +96,14 @@ def test_ownership_covers_every_tile_once():
             owned = sorted(t for r in range(world) for t in tiles_of_rank(T, r, world))
             assert owned == list(range(T))
             assert max(len(tiles_of_rank(T, r, world)) for r in range(world)) == tile_slots(T, world) >= 1
-    # 49 tiles over 8 ranks: 7,6,6,6,6,6,6,6 -> 87.5 % ideal efficiency (SURVEY.md hard part 7)
+    # 49 whole tiles over 8 ranks: 7,6,..,6 tiles = 14 / 12 forwards -> 87.5 % ideal efficiency; the 98
+    # (tile, CFG branch) units the sampler shards instead: 13,13,12,..,12 -> 94 %
     assert [len(tiles_of_rank(49, r, 8)) for r in range(8)] == [7] + [6] * 7
+    assert [len(tiles_of_rank(98, r, 8)) for r in range(8)] == [13, 13] + [12] * 6
 
 
 # ---- batch sharding (BASELINE configs[4]: images x CFG branches over the ranks) -----------------
 def _unit_worker(rank, world, port, q, B):
-    from diffbir_b200.sampler.sampler import assemble_units
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = torch.Generator().manual_seed(1)
