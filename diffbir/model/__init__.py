@@ -1,5 +1,5 @@
 """diffbir.model (reference model/__init__.py:1-12) -> diffbir_b200.model."""
-from diffbir_b200.model import ControlLDM, Diffusion, RRDBNet, SwinIR  # noqa: F401
+from diffbir_b200.model import ControlLDM, Diffusion, RRDBNet, SCUNet, SwinIR  # noqa: F401
 
 from .._unsupported import unsupported
 from . import config  # noqa: F401
@@ -9,4 +9,3 @@ ControlledUnetModel = unsupported("ControlledUnetModel", "model/controlnet.py:16
 ControlNet = unsupported("ControlNet", "model/controlnet.py:50-328", _inside)
 AutoencoderKL = unsupported("AutoencoderKL", "model/vae.py:562-582", _inside)
 FrozenOpenCLIPEmbedder = unsupported("FrozenOpenCLIPEmbedder", "model/clip.py:9-61", _inside)
-SCUNet = unsupported("SCUNet", "model/scunet.py:163-264", "use SwinIR as the stage-1 cleaner")

@@ -376,3 +376,51 @@ def rrdbnet_shapes(cfg: dict) -> Shapes:
     s["conv_last.weight"] = (cfg["out_nc"], nf, 3, 3)
     s["conv_last.bias"] = (cfg["out_nc"],)
     return s
+
+
+# ------------------------------------------------------------------------------- SCUNet
+SCUNET_CFG = dict(in_nc=3, config=(4, 4, 4, 4, 4, 4, 4), dim=64)       # configs/inference/scunet.yaml
+
+
+def scunet_stages(cfg: dict):
+    """(module name, channels = conv_dim + trans_dim, number of ConvTransBlocks, first index inside the module)
+    for the seven stages of SCUNet (model/scunet.py:176-212); the up stages start with their ConvTranspose2d."""
+    d, n = cfg["dim"], cfg["config"]
+    return [("m_down1", d, n[0], 0), ("m_down2", 2 * d, n[1], 0), ("m_down3", 4 * d, n[2], 0), ("m_body", 8 * d, n[3], 0),
+            ("m_up3", 4 * d, n[4], 1), ("m_up2", 2 * d, n[5], 1), ("m_up1", d, n[6], 1)]
+
+
+def scunet_shapes(cfg: dict) -> Shapes:
+    """state_dict of the reference's SCUNet (model/scunet.py:163-219)."""
+    d = cfg["dim"]
+    s: Shapes = OrderedDict()
+    s["m_head.0.weight"] = (d, cfg["in_nc"], 3, 3)
+    for name, c, nblk, first in scunet_stages(cfg):
+        if first:                                                  # ConvTranspose2d(2c -> c, 2, 2): [Cin, Cout, 2, 2]
+            s[f"{name}.0.weight"] = (2 * c, c, 2, 2)
+        t = c // 2                                                 # conv_dim == trans_dim
+        for i in range(nblk):
+            p = f"{name}.{first + i}."
+            s[p + "trans_block.ln1.weight"] = (t,)
+            s[p + "trans_block.ln1.bias"] = (t,)
+            s[p + "trans_block.msa.relative_position_params"] = (t // 32, 15, 15)
+            s[p + "trans_block.msa.embedding_layer.weight"] = (3 * t, t)
+            s[p + "trans_block.msa.embedding_layer.bias"] = (3 * t,)
+            s[p + "trans_block.msa.linear.weight"] = (t, t)
+            s[p + "trans_block.msa.linear.bias"] = (t,)
+            s[p + "trans_block.ln2.weight"] = (t,)
+            s[p + "trans_block.ln2.bias"] = (t,)
+            s[p + "trans_block.mlp.0.weight"] = (4 * t, t)
+            s[p + "trans_block.mlp.0.bias"] = (4 * t,)
+            s[p + "trans_block.mlp.2.weight"] = (t, 4 * t)
+            s[p + "trans_block.mlp.2.bias"] = (t,)
+            s[p + "conv1_1.weight"] = (c, c, 1, 1)
+            s[p + "conv1_1.bias"] = (c,)
+            s[p + "conv1_2.weight"] = (c, c, 1, 1)
+            s[p + "conv1_2.bias"] = (c,)
+            s[p + "conv_block.0.weight"] = (t, t, 3, 3)
+            s[p + "conv_block.2.weight"] = (t, t, 3, 3)
+        if name.startswith("m_down"):                              # Conv2d(c -> 2c, 2, 2)
+            s[f"{name}.{nblk}.weight"] = (2 * c, c, 2, 2)
+    s["m_tail.0.weight"] = (cfg["in_nc"], d, 3, 3)
+    return s

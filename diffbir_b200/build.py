@@ -3,7 +3,7 @@
     python -m diffbir_b200.build [--bf16] [--force] [-DNAME ...]
 
 Extra -D switches (also from $DBIR_BUILD_DEFS) select compile-time experiments, e.g.
--DDBIR_GEMM_EARLY_B (weight tiles requested before griddepcontrol.wait) or -DDBIR_ATTN_PROBE.
+-DDBIR_DEBUG_PROBES -DDBIR_ATTN_PROBE (calibration probes: tools/gpu_mma_rate.py, tools/gpu_attn_probe.py).
 
 Objects go to diffbir_b200/csrc/_build/, the library to diffbir_b200/libdiffbir_b200.so
 (git-ignored; it travels to the GPU box with the gpurun snapshot). --bf16 builds the bf16-operand

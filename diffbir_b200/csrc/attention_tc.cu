@@ -31,10 +31,6 @@ constexpr int KV_BYTES = TK * DH * 2;      // 8 KB per K or V step
 constexpr int P_BYTES = TQ * TK * 2;       // 16 KB
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t TM_S = 0, TM_O = 128;   // S[0] @0, S[1] @64, O @128
-// -DDBIR_ATTN_P_TMEM (next-round experiment, not compiled by default): P stays in TMEM (two 32-column
-// buffers of packed 16-bit pairs at columns 192 / 224) and is the TS-mode A operand of PV: no
-// shared-memory round trip or async-proxy fence, PV MMAs at ~42 instead of ~75 cycles.
-constexpr uint32_t TM_P = 192;
 constexpr float RESCALE_LOG2 = 8.0f;
 #ifdef DBIR_ATTN_PROBE
 constexpr bool PROBE = true;     // clock64 phase sums for tools/gpu_attn_probe.py
@@ -206,14 +202,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
           const uint64_t v_desc = v_desc0 + static_cast<uint64_t>((st * KV_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < TK / 16; ++k) {
-#ifdef DBIR_ATTN_P_TMEM
-            (void)p_desc;
-            umma_f16_ts(tmem_base + TM_O, tmem_base + TM_P + (it & 1) * 32 + 8 * k,
-                        v_desc + static_cast<uint64_t>((k * 16 * 128) >> 4), idesc_o, (jl > 0 || k != 0) ? 1u : 0u);
-#else
             umma_f16(tmem_base + TM_O, p_desc + 2 * k, v_desc + static_cast<uint64_t>((k * 16 * 128) >> 4), idesc_o,
                      (jl > 0 || k != 0) ? 1u : 0u);
-#endif
           }
           umma_commit(&bar->o_full[it & 1]);
           umma_commit(&bar->kv_empty[st]);
@@ -299,12 +289,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         if (PROBE && p.dbg) c2s = clock64();
         if (it >= 2) mbar_wait(&bar->o_full[bsel], ((it - 2) >> 1) & 1);
         if (PROBE && p.dbg) c3s = clock64();
-#ifdef DBIR_ATTN_P_TMEM
-        uint32_t pk[TK / 2];                       // P row as packed 16-bit pairs -> TMEM columns
-        (void)sw;
-#else
         uint8_t* p_row = sP + bsel * P_BYTES + r * 128;
-#endif
         const float nmb = -m_ref * sl2;
         float ls[8];
 #pragma unroll
@@ -322,14 +307,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
               ex[i + 1] = ex2_approx(x1);
               fadd2(ls[i], ls[i + 1], ls[i], ls[i + 1], ex[i], ex[i + 1]);
             }
-#ifdef DBIR_ATTN_P_TMEM
-            pk[(c0 >> 1) + 0] = pack2(ex[0], ex[1]); pk[(c0 >> 1) + 1] = pack2(ex[2], ex[3]);
-            pk[(c0 >> 1) + 2] = pack2(ex[4], ex[5]); pk[(c0 >> 1) + 3] = pack2(ex[6], ex[7]);
-#else
             uint4 t;
             t.x = pack2(ex[0], ex[1]); t.y = pack2(ex[2], ex[3]); t.z = pack2(ex[4], ex[5]); t.w = pack2(ex[6], ex[7]);
             *reinterpret_cast<uint4*>(p_row + (((c0 >> 3) ^ sw) << 4)) = t;      // 128-byte swizzle
-#endif
           }
         } else {
 #pragma unroll
@@ -341,26 +321,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
               ex[i] = c0 + i < valid ? x : 0.f;
               ls[i] += ex[i];
             }
-#ifdef DBIR_ATTN_P_TMEM
-            pk[(c0 >> 1) + 0] = pack2(ex[0], ex[1]); pk[(c0 >> 1) + 1] = pack2(ex[2], ex[3]);
-            pk[(c0 >> 1) + 2] = pack2(ex[4], ex[5]); pk[(c0 >> 1) + 3] = pack2(ex[6], ex[7]);
-#else
             uint4 t;
             t.x = pack2(ex[0], ex[1]); t.y = pack2(ex[2], ex[3]); t.z = pack2(ex[4], ex[5]); t.w = pack2(ex[6], ex[7]);
             *reinterpret_cast<uint4*>(p_row + (((c0 >> 3) ^ sw) << 4)) = t;
-#endif
           }
         }
         l_run += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
-#ifdef DBIR_ATTN_P_TMEM
-        __syncwarp();
-        tmem_st32(t_lane + TM_P + bsel * 32, pk);
-        tmem_st_wait();
-        tc_fence_before();
-#else
         tc_fence_before();
         fence_proxy_async_smem();
-#endif
         mbar_arrive(&bar->p_full[bsel]);
         if (PROBE && p.dbg) { d_ws += c1s - c0s; d_ld += c2s - c1s; d_wo += c3s - c2s; d_exp += clock64() - c3s; }
       }

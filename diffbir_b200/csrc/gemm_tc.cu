@@ -342,31 +342,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();        // the next kernel may start its prologue
-#ifdef DBIR_GEMM_EARLY_B
-  // (next-round experiment, not compiled by default) The B operand is a weight and does not depend
-  // on the predecessor kernel: its first stages are requested before griddepcontrol.wait, so under
-  // programmatic dependent launch the (cold, HBM) weight fetch overlaps the predecessor's tail.
-  const int early_total = (kb1 - kb0 + KSUB - 1) / KSUB;
-  const int early_iters = early_total < STAGES ? early_total : STAGES;
-  if (warp == 0) {
-    if (elect_one()) {
-      const uint32_t fbar_e = PAIR ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
-      const int b_row_e = grp_off + n_tile * BN + static_cast<int>(cta_rank) * B_ROWS;
-      for (int it = 0; it < early_iters; ++it) {
-        if (cta_rank == 0) mbar_expect_tx(&full[it], (PAIR ? 2 : 1) * (A_STAGE_BYTES + B_STAGE_BYTES));
-#pragma unroll
-        for (int j = 0; j < KSUB; ++j) {
-          const int kb = kb0 + it * KSUB + j;
-          const int kcb = kb < kb1 ? kb * BK : p.num_kb * BK;
-          uint8_t* b_dst = sB + it * B_STAGE_BYTES + j * B_SUB_BYTES;
-          if constexpr (PAIR) tma_load_2d_pair(b_dst, &tma_b, fbar_e + it * 8, kcb, b_row_e);
-          else tma_load_2d(b_dst, &tma_b, &full[it], kcb, b_row_e);
-        }
-      }
-    }
-    __syncwarp();
-  }
-#endif
   pdl_wait();           // A operand / residual come from predecessor kernels
   if (p.dbg) t_setup = clock64();
 
@@ -408,12 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_wait(&empty[s], ph ^ 1);
       if (elect_one()) {
         // PAIR: both CTAs' loads complete on the leader's barrier, which expects the bytes of both
-#ifdef DBIR_GEMM_EARLY_B
-        const bool b_done = it < early_iters;         // B of this stage was requested before the PDL wait
-#else
-        constexpr bool b_done = false;
-#endif
-        if (cta_rank == 0 && !b_done) mbar_expect_tx(&full[s], (PAIR ? 2 : 1) * (A_STAGE_BYTES + B_STAGE_BYTES));
+        if (cta_rank == 0) mbar_expect_tx(&full[s], (PAIR ? 2 : 1) * (A_STAGE_BYTES + B_STAGE_BYTES));
         const uint32_t fbar = fbar0 + s * 8;
 #pragma unroll
         for (int j = 0; j < KSUB; ++j) {
@@ -426,10 +396,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if constexpr (PAIR) tma_load_4d_pair(a_dst, &tma_a, fbar, ac[j], ax[j], ay[j], n0);
             else tma_load_4d(a_dst, &tma_a, &full[s], ac[j], ax[j], ay[j], n0);
           }
-          if (!b_done) {
-            if constexpr (PAIR) tma_load_2d_pair(b_dst, &tma_b, fbar, kc[j], b_row);
-            else tma_load_2d(b_dst, &tma_b, &full[s], kc[j], b_row);
-          }
+          if constexpr (PAIR) tma_load_2d_pair(b_dst, &tma_b, fbar, kc[j], b_row);
+          else tma_load_2d(b_dst, &tma_b, &full[s], kc[j], b_row);
         }
       }
       __syncwarp();

@@ -24,7 +24,7 @@ template <int HEADS, int DH>
 __global__ void __launch_bounds__(NTOK)
 swin_window_attn_kernel(const op_t* __restrict__ qkv, long long ldq, int H, int W, int shift,
                         const float* __restrict__ bias_table, op_t* __restrict__ out,
-                        long long ldo) {
+                        long long ldo, float mask_value) {
   constexpr int C = HEADS * DH;
   constexpr int DP = 32;                          // DH padded for float4 rows
   static_assert(DH <= DP && DH % 2 == 0, "head_dim must be even and <= 32");
@@ -94,7 +94,7 @@ swin_window_attn_kernel(const op_t* __restrict__ qkv, long long ldq, int H, int 
     }
     float acc = (a0 + a1) + (a2 + a3);
     acc += s_bias[bias_base - ((j / WS) * (2 * WS - 1) + (j % WS))];
-    if ((masked >> j) & 1ull) acc += -100.0f;
+    if ((masked >> j) & 1ull) acc += mask_value;       // -100 (SwinIR, swinir.py:241) or -inf (SCUNet, scunet.py:77)
     sc[j] = acc;
     m = fmaxf(m, acc);
   }
@@ -123,19 +123,35 @@ swin_window_attn_kernel(const op_t* __restrict__ qkv, long long ldq, int H, int 
 
 }  // namespace
 
+extern "C" int dbir_window_attention(const void* qkv, int64_t ldq, int32_t batch, int32_t h, int32_t w, int32_t heads,
+                                     int32_t head_dim, int32_t window, int32_t shift, const float* bias_table,
+                                     float mask_value, void* out, int64_t ldo, void* stream) {
+  DBIR_REQUIRE(qkv && bias_table && out, "dbir_window_attention: null pointer");
+  DBIR_REQUIRE(window == 8, "dbir_window_attention: built for 8 x 8 windows");
+  DBIR_REQUIRE(h % 8 == 0 && w % 8 == 0 && ldq % 2 == 0 && ldo % 2 == 0 && shift >= 0 && shift < 8,
+               "dbir_window_attention: bad geometry");
+  const int nwin = batch * (h / 8) * (w / 8);
+#define DBIR_WIN(H_, D_)                                                                                             \
+  if (heads == H_ && head_dim == D_) {                                                                                \
+    DBIR_CHECK_CUDA(dbir_launch(swin_window_attn_kernel<H_, D_>, dim3(nwin * H_), dim3(NTOK), 0,                      \
+                                reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const op_t*>(qkv),          \
+                                static_cast<long long>(ldq), h, w, shift, bias_table, reinterpret_cast<op_t*>(out),   \
+                                static_cast<long long>(ldo), mask_value));                                            \
+    return 0;                                                                                                         \
+  }
+  DBIR_WIN(6, 30)      // SwinIR stage 1 (configs/inference/swinir.yaml)
+  DBIR_WIN(1, 32)      // SCUNet levels: trans_dim 32 / 64 / 128 / 256, head_dim 32 (scunet.py:167-168)
+  DBIR_WIN(2, 32)
+  DBIR_WIN(4, 32)
+  DBIR_WIN(8, 32)
+#undef DBIR_WIN
+  dbir_set_error("dbir_window_attention: unsupported heads x head_dim %d x %d", heads, head_dim);
+  return -2;
+}
+
 extern "C" int dbir_swin_window_attention(const void* qkv, int64_t ldq, int32_t batch, int32_t h,
                                           int32_t w, int32_t heads, int32_t head_dim,
                                           int32_t window, int32_t shift, const float* bias_table,
                                           void* out, int64_t ldo, void* stream) {
-  DBIR_REQUIRE(qkv && bias_table && out, "dbir_swin_window_attention: null pointer");
-  DBIR_REQUIRE(window == 8 && heads == 6 && head_dim == 30,
-               "dbir_swin_window_attention: built for window 8, 6 heads x 30 (configs/inference/swinir.yaml)");
-  DBIR_REQUIRE(h % 8 == 0 && w % 8 == 0 && ldq % 2 == 0 && ldo % 2 == 0 && shift >= 0 && shift < 8,
-               "dbir_swin_window_attention: bad geometry");
-  const int nwin = batch * (h / 8) * (w / 8);
-  DBIR_CHECK_CUDA(dbir_launch(swin_window_attn_kernel<6, 30>, dim3(nwin * 6), dim3(NTOK), 0,
-                              reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const op_t*>(qkv),
-                              static_cast<long long>(ldq), h, w, shift, bias_table, reinterpret_cast<op_t*>(out),
-                              static_cast<long long>(ldo)));
-  return 0;
+  return dbir_window_attention(qkv, ldq, batch, h, w, heads, head_dim, window, shift, bias_table, -100.0f, out, ldo, stream);
 }

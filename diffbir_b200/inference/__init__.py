@@ -1,7 +1,8 @@
 """diffbir.inference counterpart: the inference loops whose networks are on the accelerated path.
-BID (SCUNet cleaner), unaligned faces (face detector) and custom loops are refused by the CLI."""
+Unaligned faces (face detector) and custom loops are refused by the CLI."""
 from .bfr_loop import BFRInferenceLoop
+from .bid_loop import BIDInferenceLoop
 from .bsr_loop import BSRInferenceLoop
 from .loop import InferenceLoop
 
-__all__ = ["InferenceLoop", "BSRInferenceLoop", "BFRInferenceLoop"]
+__all__ = ["InferenceLoop", "BSRInferenceLoop", "BFRInferenceLoop", "BIDInferenceLoop"]

@@ -13,6 +13,7 @@ MODELS: Dict[str, str] = {
     "swinir_face": "face_swinir_v1.ckpt",
     "swinir_realesrgan": "realesrgan_s4_swinir_100k.pth",
     "bsrnet": "BSRNet.pth",
+    "scunet_psnr": "scunet_color_real_psnr.pth",
     # Stable Diffusion 2.1 base (UNet + VAE + OpenCLIP text tower)
     "sd_v2.1": "v2-1_512-ema-pruned.ckpt",
     "sd_v2.1_zsnr": "sd2.1-base-zsnr-laionaes5.ckpt",
@@ -22,8 +23,7 @@ MODELS: Dict[str, str] = {
     "v2": "v2.pth",
     "v2.1": "DiffBIR_v2.1.pt",
 }
-# cleaners of the reference registry whose networks are outside this package's path
-UNSUPPORTED = {"scunet_psnr": "scunet_color_real_psnr.pth"}
+UNSUPPORTED: Dict[str, str] = {}      # (every cleaner of the reference registry is built)
 
 
 def default_weights_dir() -> str:

@@ -273,6 +273,12 @@ def layernorm(x, ldx, rows, c, gamma, beta, out, ldo, eps=1e-5, rows_per_group=0
     count_launch()
 
 
+def window_attention(qkv, ldq, batch, h, w, heads, head_dim, shift, bias_table, mask_value, out, ldo):
+    check(load().dbir_window_attention(_fp(qkv), C.c_int64(ldq), batch, h, w, heads, head_dim, 8, shift, _fp(bias_table),
+                                       C.c_float(mask_value), _fp(out), C.c_int64(ldo), _sp()), "dbir_window_attention")
+    count_launch()
+
+
 def swin_window_attention(qkv, ldq, batch, h, w, shift, bias_table, out, ldo):
     check(load().dbir_swin_window_attention(_fp(qkv), C.c_int64(ldq), batch, h, w, 6, 30, 8, shift,
                                             _fp(bias_table), _fp(out), C.c_int64(ldo), _sp()),

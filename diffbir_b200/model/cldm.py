@@ -45,6 +45,10 @@ class ControlLDM:
         self._ctx_ref = None      # (tensor, version) the engine's cross-attention K/V were built from
         self._t_key = None
         self._txt_cache: Dict[str, torch.Tensor] = {}   # prompt -> [77, D] text-tower output (see encode_text)
+        # True: VAE encode / decode are sharded by image rows over the torch.distributed ranks (all ranks must pass
+        # the same tensors; set by the pipeline while ranks cooperate on one job: tiled / batch-sharded sampling)
+        self.shard_vae = False
+        self._svae = None
 
     # --------------------------------------------------------------- checkpoint loaders
     @torch.no_grad()
@@ -87,6 +91,7 @@ class ControlLDM:
         self.engine = self.vae = self.clip = None
         self._ctx_ref = self._t_key = None
         self._txt_cache = {}
+        self._svae = None
 
     def _build(self):
         if self.engine is None:
@@ -153,7 +158,9 @@ class ControlLDM:
         self._build()
         if tiled:
             raise NotImplementedError("tiled VAE (utils/tilevae) is outside the B200 hot path: 180 GB HBM")
-        m = self.vae.encode_moments(image.to(self.device, torch.float32).contiguous())
+        image = image.to(self.device, torch.float32).contiguous()
+        sv = self._sharded_vae(image.shape[2], image.shape[3])
+        m = sv.encode_moments(image) if sv is not None else self.vae.encode_moments(image)
         mean, logvar = m.chunk(2, dim=1)
         if sample:   # DiagonalGaussianDistribution.sample, model/distributions.py:25-37
             std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
@@ -165,7 +172,20 @@ class ControlLDM:
         self._build()
         if tiled:
             raise NotImplementedError("tiled VAE (utils/tilevae) is outside the B200 hot path: 180 GB HBM")
-        return self.vae.decode((z / self.scale_factor).to(self.device, torch.float32).contiguous())
+        z = (z / self.scale_factor).to(self.device, torch.float32).contiguous()
+        sv = self._sharded_vae(8 * z.shape[2], 8 * z.shape[3])
+        return sv.decode(z) if sv is not None else self.vae.decode(z)
+
+    def _sharded_vae(self, h_img: int, w_img: int):
+        """The row-sharded VAE (engine.vae_sharded) when ranks cooperate on this job and the size allows it."""
+        if not self.shard_vae:
+            return None
+        from ..engine.vae_sharded import ShardedVae
+        if not ShardedVae.usable(h_img, w_img):
+            return None
+        if self._svae is None:
+            self._svae = ShardedVae(self.vae)
+        return self._svae
 
     @torch.no_grad()
     def prepare_condition(self, cond_img: torch.Tensor, txt: List[str], tiled: bool = False,

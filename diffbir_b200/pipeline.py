@@ -46,6 +46,7 @@ class Pipeline:
         self.output_size: Tuple[int, int] = None
         self.taps: Optional[dict] = None   # set to {} to capture intermediates (tests)
         self.fused_post = True             # colour fix + quantisation as one kernel (False: the torch op sequence)
+        self.shard_vae = True              # cooperating ranks (tiled / batch-sharded sampling) shard the VAE by image rows
         self.shard_batch = False           # un-tiled batches: shard (image, CFG branch) forwards over torch.distributed ranks
         self.marks: Optional[list] = None  # set to [] to record (phase, CUDA event) boundaries (bench.py phases_ms)
 
@@ -81,6 +82,10 @@ class Pipeline:
             raise NotImplementedError("tiled VAE is outside the B200 hot path (180 GB HBM per GPU)")
         bs, _, h0, w0 = cond_img.shape
         cond_img = pad_to_multiples_of(cond_img, multiple=8 if cldm_tiled else 64)
+        # ranks that cooperate on this job (sharded tiles or batch units) also shard the VAE by image rows
+        import torch.distributed as dist
+        coop = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and (cldm_tiled or self.shard_batch)
+        self.cldm.shard_vae = bool(coop and self.shard_vae)
         # The reference encodes the (identical) condition image twice (pipeline.py:117-128);
         # the latent is deterministic (posterior mode), so it is encoded once and shared.
         # Both prompts go through the text tower as one batch (pipeline.py:117-128 runs it twice).
@@ -131,6 +136,7 @@ class Pipeline:
         self._mark("sampler_loop")
         z = z[..., :h1, :w1].contiguous()
         x = self.cldm.vae_decode(z)
+        self.cldm.shard_vae = False
         self._mark("vae_decode")
         x = x[:, :, :h0, :w0]
         self.cldm.control_scales = control_scales
@@ -242,3 +248,18 @@ class BSRNetPipeline(Pipeline):
         if min(self.output_size) < 512:
             return resize_short_edge_to(up4, size=512)
         return F.interpolate(up4, size=self.output_size, mode="bicubic", antialias=True)
+
+
+class SCUNetPipeline(Pipeline):
+    """pipeline.py:400-420: the v2 blind-denoising recipe. Stage 1 is SCUNet on the (pre-upscaled) LQ image, optionally
+    over Gaussian-blended tiles; outputs under 512 are resized to short edge 512."""
+
+    def apply_cleaner(self, lq: torch.Tensor, tiled: bool, tile_size: int, tile_stride: int) -> torch.Tensor:
+        if tiled and (lq.size(2) < tile_size or lq.size(3) < tile_size):
+            print("[SCUNet]: the input size is tiny and unnecessary to tile.")
+            tiled = False
+        model = make_tiled_fn(self.cleaner, tile_size, tile_stride) if tiled else self.cleaner
+        output = model(lq)
+        if min(output.shape[2:]) < 512:
+            output = resize_short_edge_to(output, size=512)
+        return output

@@ -146,6 +146,12 @@ int dbir_layernorm(const float* x, int64_t ldx, int32_t rows, int32_t c, const f
 int dbir_swin_window_attention(const void* qkv, int64_t ldq, int32_t batch, int32_t h, int32_t w,
                                int32_t heads, int32_t head_dim, int32_t window, int32_t shift,
                                const float* bias_table, void* out, int64_t ldo, void* stream);
+/* Same kernel for other (heads, head_dim) pairs -- 6 x 30 (SwinIR) and {1,2,4,8} x 32 (SCUNet's WMSA, scunet.py:9-99:
+ * same roll / window / relative-position-bias / region-mask structure) -- and an explicit mask value added to the
+ * logits of token pairs from different shift regions (-100 in SwinIR, -inf in SCUNet). */
+int dbir_window_attention(const void* qkv, int64_t ldq, int32_t batch, int32_t h, int32_t w, int32_t heads,
+                          int32_t head_dim, int32_t window, int32_t shift, const float* bias_table, float mask_value,
+                          void* out, int64_t ldo, void* stream);
 
 /* ---- small / memory-bound ops ------------------------------------------------------------
  * conv3x3_small_cin : stems with <= 16 input channels; input = virtual concat of two NCHW

@@ -190,3 +190,34 @@ def test_rrdbnet_full_config_vs_oracle():
     e = rel_rms(y, ref)
     print(f"rrdbnet full: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB, |y| {ref.abs().mean():.4f}")
     assert y.shape == (1, 3, 512, 640) and e < TOL
+
+
+def test_scunet_small_vs_reference_golden(golden_dir):
+    from diffbir_b200.model import SCUNet
+    from tests.small_cfg import SCUNET_SMALL
+    no_tf32()
+    g = np.load(golden_dir / "scunet_small.npz")
+    net = SCUNet(**SCUNET_SMALL, device="cuda")
+    net.load_state_dict(make_state_dict(arch.scunet_shapes(SCUNET_SMALL), 9))
+    y = net(torch.from_numpy(g["x"]).cuda())                 # 120 x 72: replicate-padded to 128 x 128 inside
+    ref = torch.from_numpy(g["y"]).cuda()
+    e = rel_rms(y, ref)
+    print(f"scunet small vs reference: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB")
+    assert y.shape == ref.shape and e < TOL
+    assert torch.equal(y, net(torch.from_numpy(g["x"]).cuda()))
+
+
+def test_scunet_full_config_vs_oracle():
+    """SCUNet [4,4,4,4,4,4,4] x dim 64 (configs/inference/scunet.yaml) on a 256 x 320 image against the fp32 oracle."""
+    from diffbir_b200.engine.scunet import SCUNetEngine
+    from oracle import scunet as osc
+    no_tf32()
+    sd = make_state_dict(arch.scunet_shapes(arch.SCUNET_CFG), 79)
+    eng = SCUNetEngine(sd, None, "cuda")
+    x = torch.rand(1, 3, 256, 320, generator=torch.Generator().manual_seed(6)).cuda()
+    y = eng.forward(x)
+    with torch.no_grad():
+        ref = osc.scunet_forward(to_dev(sd), x)
+    e = rel_rms(y, ref)
+    print(f"scunet full: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB, |y| {ref.abs().mean():.4f}")
+    assert y.shape == x.shape and e < TOL

@@ -259,7 +259,9 @@ def test_diffbir_alias_exposes_the_reference_names():
             assert hasattr(mod, n), f"{mod.__name__}.{n} missing"
     assert dsm.EDMSampler is diffbir_b200.sampler.EDMSampler and dsm.DPMSolverSampler is diffbir_b200.sampler.DPMSolverSampler
     assert dm.RRDBNet is diffbir_b200.model.RRDBNet and dp.BSRNetPipeline is diffbir_b200.pipeline.BSRNetPipeline
-    for cls in (dp.SCUNetPipeline, dm.SCUNet, di.BIDInferenceLoop):
+    assert dm.SCUNet is diffbir_b200.model.SCUNet and dp.SCUNetPipeline is diffbir_b200.pipeline.SCUNetPipeline
+    assert di.BIDInferenceLoop is diffbir_b200.inference.BIDInferenceLoop
+    for cls in (di.UnAlignedBFRInferenceLoop, di.CustomInferenceLoop, dm.ControlNet):
         with pytest.raises(NotImplementedError):
             cls()
     # the YAML reflection targets of the reference configs resolve through the alias too

@@ -54,7 +54,7 @@ def test_checkpoints_resolve_locally_and_fail_loudly(tmp_path):
         resolve("v2.1", str(tmp_path))
     (tmp_path / "DiffBIR_v2.1.pt").write_bytes(b"x")
     assert resolve("v2.1", str(tmp_path)).endswith("DiffBIR_v2.1.pt")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError, match="scunet_color_real_psnr.pth"):
         resolve("scunet_psnr", str(tmp_path))
     with pytest.raises(FileNotFoundError, match="BSRNet.pth"):
         resolve("bsrnet", str(tmp_path))

@@ -181,3 +181,21 @@ def test_rrdbnet_and_bsrnet_cleaner_match_reference(golden_dir):
             pipe.set_output_size(lq.size())
             b = pipe.apply_cleaner(lq, False, 512, 256)
             np.testing.assert_array_equal(b.numpy(), a.numpy())
+
+
+def test_scunet_matches_reference(golden_dir):
+    """oracle.scunet (SCUNet.forward incl. the replicate pad / crop and both block types) against a fixture the
+    reference module produced, bit-exact; SCUNetPipeline's host code on top of it."""
+    from diffbir_b200.pipeline import SCUNetPipeline
+    from oracle import scunet as osc
+    from tests.small_cfg import SCUNET_SMALL
+    g = np.load(golden_dir / "scunet_small.npz")
+    sd = make_state_dict(arch.scunet_shapes(SCUNET_SMALL), 9)
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        y = osc.scunet_forward(sd, x)
+        np.testing.assert_array_equal(y.numpy(), g["y"])
+        net = lambda im: osc.scunet_forward(sd, im)           # noqa: E731
+        pipe = SCUNetPipeline(net, None, None, None, "cpu")
+        a, b = pipe.apply_cleaner(x, False, 512, 256), osc.scunet_apply_cleaner(net, x)
+        assert a.shape[2:] == (853, 512) and torch.equal(a, b)
