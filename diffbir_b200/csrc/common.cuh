@@ -82,14 +82,13 @@ extern "C" int dbir_sm_count(void);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------
-// Programmatic dependent launch (PDL): kernels of the step loop are launched with the
-// programmatic-stream-serialization attribute; each one calls pdl_trigger() as soon as its CTA is
-// set up (lets the NEXT kernel's CTAs be scheduled and run their prologue: barrier init, TMEM
-// alloc, descriptor prefetch) and pdl_wait() before touching memory written by its predecessors
-// (griddepcontrol.wait returns when all prerequisite grids completed and flushed). Hides the
-// kernel-to-kernel latency of the ~600 dependent kernels per forward. Measured on B200 inside the
-// captured graph: 7.59 ms vs 7.65 ms per forward, i.e. the graph already hides most of it, so PDL is
-// opt-in (DBIR_PDL=1).
+// Programmatic dependent launch (PDL): every kernel is launched with the programmatic-stream-serialization
+// attribute (on by default, DBIR_PDL=0 turns it off); each one calls pdl_trigger() at entry (lets the NEXT
+// kernel's CTAs be scheduled and run their prologue: barrier init, TMEM alloc, descriptor prefetch) and
+// pdl_wait() before touching memory written by its predecessors (griddepcontrol.wait returns when all
+// prerequisite grids completed and flushed). Measured on B200 inside the captured forward graph (round 2,
+// profiles/r02_forward_ab_4.jsonl): 5.80 ms with it, 5.76 ms without -- the ~200 KB shared-memory GEMM CTAs
+// cannot co-reside with their successor's CTAs, so there is little to overlap; it is harmless and stays on.
 // ---------------------------------------------------------------------------
 extern "C" int dbir_pdl_enabled(void);
 template <typename... KArgs, typename... Args>
@@ -437,6 +436,32 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   // Phi(x) = 1 - half_erfc for x >= 0, half_erfc for x < 0
   const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
   return x * phi;
+}
+// Two GELUs per call on packed fp32 pairs (FFMA2 / FMUL2): same A-S 7.1.26 polynomial as gelu_erf_f, half the
+// FMA-pipe issue slots -- the GEGLU epilogue (K = C: the mainloop is only 5-20 k-blocks long) is bound by them.
+__device__ __forceinline__ void gelu_erf_f2(float x0, float x1, float& y0, float& y1) {
+  float z0 = fabsf(x0), z1 = fabsf(x1);
+  fmul2(z0, z1, z0, z1, 0.70710678118654752f, 0.70710678118654752f);
+  float d0, d1;
+  ffma2(d0, d1, z0, z1, 0.3275911f, 0.3275911f, 1.0f, 1.0f);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  float p0, p1;
+  ffma2(p0, p1, t0, t1, 1.061405429f, 1.061405429f, -1.453152027f, -1.453152027f);
+  ffma2(p0, p1, p0, p1, t0, t1, 1.421413741f, 1.421413741f);
+  ffma2(p0, p1, p0, p1, t0, t1, -0.284496736f, -0.284496736f);
+  ffma2(p0, p1, p0, p1, t0, t1, 0.254829592f, 0.254829592f);
+  fmul2(p0, p1, p0, p1, t0, t1);
+  float q0, q1;
+  fmul2(q0, q1, z0, z1, z0, z1);
+  fmul2(q0, q1, q0, q1, -1.4426950408889634f, -1.4426950408889634f);
+  const float e0 = ex2_approx(q0), e1 = ex2_approx(q1);
+  float h0, h1;
+  fmul2(h0, h1, p0, p1, e0, e1);
+  fmul2(h0, h1, h0, h1, 0.5f, 0.5f);                    // 0.5 * erfc(|x| / sqrt 2)
+  const float phi0 = x0 >= 0.f ? 1.0f - h0 : h0, phi1 = x1 >= 0.f ? 1.0f - h1 : h1;
+  fmul2(y0, y1, x0, x1, phi0, phi1);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -623,6 +623,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr int HB = BN / 2;
       const int n_half = p.N / 2;
       if constexpr (HB % 32 == 0) {
+        // Value / gate biases of this warp's chunks go through its (unused: GEGLU has no residual) residual
+        // staging tile and come back as broadcast LDS.128: 16 loads per chunk instead of 64 shuffles, and the
+        // gating math runs on packed fp32 pairs -- the epilogue's FMA-pipe slots bound this kernel (K = C).
+        const uint32_t bb = e.res_buf(0);
+#pragma unroll
+        for (int i = 0; i < MAX_G; ++i) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bb + (i * 64 + lane) * 4), "f"(pa[i]) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bb + (i * 64 + 32 + lane) * 4), "f"(pg[i]) : "memory");
+        }
+        __syncwarp();
         int ci = 0;
 #pragma unroll
         for (int i = 0; i < MAX_G; ++i) {
@@ -637,12 +647,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (gc0 >= n_half) continue;
           const int ncols = min(32, n_half - gc0);
           float v[32];
+#ifdef DBIR_GEGLU_SCALAR      // A/B build of the previous epilogue (shuffled biases, scalar GELU); removed after measuring
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float a = __uint_as_float(av[j]) + __shfl_sync(0xffffffffu, pa[i], j);
             const float g = __uint_as_float(ag[j]) + __shfl_sync(0xffffffffu, pg[i], j);
             v[j] = a * gelu_erf_f(g);
           }
+#else
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 ba = lds_v4(bb + i * 256 + jj * 16), bg = lds_v4(bb + i * 256 + 128 + jj * 16);
+            float a0, a1, a2, a3, g0, g1, g2, g3, y0, y1, y2, y3;
+            fadd2(a0, a1, __uint_as_float(av[4 * jj]), __uint_as_float(av[4 * jj + 1]), ba.x, ba.y);
+            fadd2(a2, a3, __uint_as_float(av[4 * jj + 2]), __uint_as_float(av[4 * jj + 3]), ba.z, ba.w);
+            fadd2(g0, g1, __uint_as_float(ag[4 * jj]), __uint_as_float(ag[4 * jj + 1]), bg.x, bg.y);
+            fadd2(g2, g3, __uint_as_float(ag[4 * jj + 2]), __uint_as_float(ag[4 * jj + 3]), bg.z, bg.w);
+            gelu_erf_f2(g0, g1, y0, y1);
+            gelu_erf_f2(g2, g3, y2, y3);
+            fmul2(v[4 * jj], v[4 * jj + 1], a0, a1, y0, y1);
+            fmul2(v[4 * jj + 2], v[4 * jj + 3], a2, a3, y2, y3);
+          }
+#endif
           finish_chunk(p, e, v, lane, ci, gc0, ncols, -1, out_row, vec_idx, false);
           ++ci;
         }
