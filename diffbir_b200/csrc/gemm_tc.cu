@@ -647,14 +647,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (gc0 >= n_half) continue;
           const int ncols = min(32, n_half - gc0);
           float v[32];
-#ifdef DBIR_GEGLU_SCALAR      // A/B build of the previous epilogue (shuffled biases, scalar GELU); removed after measuring
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = __uint_as_float(av[j]) + __shfl_sync(0xffffffffu, pa[i], j);
-            const float g = __uint_as_float(ag[j]) + __shfl_sync(0xffffffffu, pg[i], j);
-            v[j] = a * gelu_erf_f(g);
-          }
-#else
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const float4 ba = lds_v4(bb + i * 256 + jj * 16), bg = lds_v4(bb + i * 256 + 128 + jj * 16);
@@ -668,7 +660,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             fmul2(v[4 * jj], v[4 * jj + 1], a0, a1, y0, y1);
             fmul2(v[4 * jj + 2], v[4 * jj + 3], a2, a3, y2, y3);
           }
-#endif
           finish_chunk(p, e, v, lane, ci, gc0, ncols, -1, out_row, vec_idx, false);
           ++ci;
         }

@@ -51,7 +51,33 @@ def test_batch_invariance_single_gpu(small):
         eng.load_step(0)
         return eng.forward(x[:n].contiguous(), ci[:n].contiguous(), [1.0] * 13).clone()
 
-    a, b, c = run(2), run(n_max), run(4)
+    a, b, c, d = run(2), run(n_max), run(4), run(1)       # 7 and 1: odd batches take the un-grouped (two-stream) encoder
     assert torch.isfinite(a).all() and a.abs().max() > 0
-    assert torch.equal(a, b[:2]) and torch.equal(c, b[:4]), (
+    assert torch.equal(a, b[:2]) and torch.equal(c, b[:4]) and torch.equal(d, b[:1]), (
         f"batch-dependent bits: max diff {(a - b[:2]).abs().max().item():.3e}")
+
+
+def test_single_forward_per_rank_shape_of_config5():
+    """BASELINE configs[4] on 8 GPUs leaves ONE (image, CFG branch) forward of a 1024^2 image per rank: the full
+    SD-2.1 engine at batch 1, latent 128 x 128 (16 384-token self-attention), must agree with the same sample inside a
+    batch of 2 under the batch-invariant plans the sharded sampler pins."""
+    from diffbir_b200.utils.synth import build_synthetic_pipeline
+    pipe = build_synthetic_pipeline("cuda", 1234, small=False)
+    cl = pipe.cldm
+    cl._build()
+    eng = cl.engine
+    eng.batch_invariant = True
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 4, 128, 128, generator=g).cuda()
+    ci = torch.randn(2, 4, 128, 128, generator=g).cuda()
+    ctx = torch.randn(2, 77, cl.unet_cfg["context_dim"], generator=g).cuda()
+
+    def run(n):
+        eng.set_context(ctx[:n].contiguous())
+        eng.set_timesteps([700], n)
+        eng.load_step(0)
+        return eng.forward(x[:n].contiguous(), ci[:n].contiguous(), [1.0] * 13).clone()
+
+    one, two = run(1), run(2)
+    assert torch.isfinite(one).all() and one.abs().max() > 0
+    assert torch.equal(one, two[:1])
