@@ -337,6 +337,39 @@ def gpu_torch_baseline(torch, dev, n_steps: int = 3):
                       "timed and extrapolated to 50"}
 
 
+def run_leg(name: str, limit_s: int):
+    """`python bench.py --leg <name>` in a child process; its last stdout line is the leg's JSON object."""
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--leg", name], capture_output=True, text=True,
+                           timeout=limit_s)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"unavailable": f"leg exited with {r.returncode}: {(r.stderr or '')[-160:]}"}
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"not finished within its {limit_s} s limit"}
+    except Exception as ex:
+        return {"unavailable": repr(ex)[:200]}
+
+
+def leg_main(name: str):
+    if name == "gpu_torch":
+        import torch
+        torch.cuda.set_device(0)
+        print(json.dumps(gpu_torch_baseline(torch, "cuda:0")))
+    elif name == "cpu":
+        t, cores = cpu_reference_times(n_steps=1)
+        step_s = t["sampler_step"][0]
+        total = cpu_image_seconds(t, step_s)
+        print(json.dumps({"value": 512 * 512 / 1e6 / total, "unit": "MPix/s", "cores": cores, "kind": "port",
+                          "thread_probe_ms": calibrated_threads()[1], "host_threads": host_threads(),
+                          "sample": (f"oracle port, fp32: SwinIR {t['swinir']:.2f}s + VAE encode 2x{t['vae_encode']:.2f}s + "
+                                     f"1 of 50 sampler steps ({step_s:.2f}s, 2 forwards) x50 + VAE decode {t['vae_decode']:.2f}s "
+                                     f"= {total:.1f}s per 512^2 image (extrapolated)")}))
+    else:
+        raise SystemExit(f"unknown leg {name}")
+
+
 def run_ours(args):
     import numpy as np  # noqa: F401
     import torch
@@ -383,6 +416,7 @@ def run_ours(args):
             return pipe.run_device(lq_dev, **kw)
         return pipe.run(lq_pinned, **kw)
 
+    log(f"[rank {rank}] 512^2: warm-up")
     for _ in range(max(args.warmup, 3)):              # W >= 3 (timing rules)
         one(True)
     out = one(False)
@@ -421,6 +455,7 @@ def run_ours(args):
     mpix_512 = world * args.steps * 512 * 512 / 1e6
     value_512, e2e_512 = mpix_512 / (dev_ms / 1e3), mpix_512 / (e2e_ms / 1e3)
 
+    log(f"[rank {rank}] 512^2 timed: {dev_ms / args.steps:.1f} ms per image")
     # ------------------------------------------------------------------ 512^2, four images per call (throughput mode)
     b4 = None
     if not args.no_batch4:
@@ -440,6 +475,7 @@ def run_ours(args):
               "note": "same workload as `value` with 4 images per Pipeline.run call (8 forwards per graph replay): the "
                       "throughput mode of a folder run; the headline `value` keeps one image per call (latency mode)"}
 
+    log(f"[rank {rank}] batch-4 block done")
     # ------------------------------------------------------------------ tiled 2048^2 (sharded, all-gather per step)
     tiled = None
     if not args.no_tiled:
@@ -498,6 +534,7 @@ def run_ours(args):
                              "round-robin over the ranks, one NCCL all-gather of per-tile eps per step (configs[3]); SwinIR / VAE / "
                              "CLIP replicated"}
 
+    log(f"[rank {rank}] tiled-2048 block done")
     # ------------------------------------------------------------------ v2.1 1024^2 batch 4 (configs[4])
     v21 = None
     if not args.no_v21:
@@ -549,6 +586,7 @@ def run_ours(args):
                            "all-gather of eps per step (configs[4]); SwinIR / VAE / CLIP replicated; fp16 operands (the bf16 "
                            "build is DBIR_OPERANDS=bf16)"}
 
+    log(f"[rank {rank}] v2.1 block done")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -596,23 +634,18 @@ def run_ours(args):
         f.write("kind,shape,launches,gflop,ms,tflops\n")
         for k, (fl, ms, n) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[0]},{'x'.join(map(str, k[1:]))},{n},{fl / 1e9:.2f},{ms:.4f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f}\n")
+    log("[rank 0] kernel census done")
     # ---- baselines on the same box, N = 1 only ------------------------------------------------
     cpu = gpu_base = None
     if world == 1 and not args.no_cpu_baseline:
+        # The two informational baselines run as child processes with a time limit each: a stall in one of them
+        # (a cold cuDNN page-in took 6 minutes on one box) must not cost the line its measured numbers.
         del pipe
         torch.cuda.empty_cache()
-        try:
-            gpu_base = gpu_torch_baseline(torch, dev)
-        except Exception as ex:                                   # informational only
-            gpu_base = {"unavailable": repr(ex)[:200]}
-        t, cores = cpu_reference_times(n_steps=1)
-        step_s = t["sampler_step"][0]
-        total = cpu_image_seconds(t, step_s)
-        cpu = {"value": 512 * 512 / 1e6 / total, "unit": "MPix/s", "cores": cores, "kind": "port",
-               "thread_probe_ms": calibrated_threads()[1], "host_threads": host_threads(),
-               "sample": (f"oracle port, fp32: SwinIR {t['swinir']:.2f}s + VAE encode 2x{t['vae_encode']:.2f}s + "
-                          f"1 of 50 sampler steps ({step_s:.2f}s, 2 forwards) x50 + VAE decode {t['vae_decode']:.2f}s "
-                          f"= {total:.1f}s per 512^2 image (extrapolated)")}
+        gpu_base = run_leg("gpu_torch", 300)
+        log(f"[rank 0] GPU torch baseline: {str(gpu_base)[:200]}")
+        cpu = run_leg("cpu", 420)
+        log(f"[rank 0] CPU baseline: {str(cpu)[:200]}")
     wl_512 = "BSR pipeline 512x512, 50-step spaced sampler, cfg 4.0, random-init SD2.1 UNet+ControlNet (configs[1])"
     line = {
         "metric": METRIC, "value": value_512, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
@@ -661,8 +694,11 @@ def main():
     ap.add_argument("--no-v21", action="store_true", help="skip the v2.1 1024^2 batch-4 block")
     ap.add_argument("--no-batch4", action="store_true", help="skip the 4-images-per-call 512^2 block")
     ap.add_argument("--tiled-images", type=int, default=1)
+    ap.add_argument("--leg", default="", help=argparse.SUPPRESS)      # internal: one baseline leg in a child process
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.leg:
+        leg_main(args.leg)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

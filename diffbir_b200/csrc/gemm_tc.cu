@@ -171,33 +171,33 @@ __device__ __forceinline__ void finish_chunk(const GemmParams& p, EpiCtx& e, flo
       for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
     }
   } else if (raw_math) {
-    if (p.bias) {
-      if (p.bias_per_row) {
-        const float bv = out_row >= 0 ? __ldg(p.bias + out_row) : 0.f;
+    if (p.bias && p.bias_per_row) {
+      const float bv = out_row >= 0 ? __ldg(p.bias + out_row) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += bv;
-      } else if (ncols == 32) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + e.grp_off + gc0 + j));
-          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + e.grp_off + gc0 + j);
-      }
-    }
-    if (p.rowvec && out_row >= 0) {
+      for (int j = 0; j < 32; ++j) v[j] += bv;
+    } else if (p.bias || p.rowvec) {
+      // acc + (bias + rowvec): the same association as the prefetched path above, so a sample's bits do not
+      // depend on whether its warp's 32 rows share one row vector (tiny images: several images per warp)
+      const bool rv_on = p.rowvec && out_row >= 0;
       const float* rv = p.rowvec + static_cast<long long>(vec_idx) * p.N + gc0;
       if (ncols == 32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(rv + j));
+          float4 t = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + e.grp_off + gc0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rv_on) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(rv + j));
+            t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+          }
           v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(rv + j);
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) {
+            float t = p.bias ? __ldg(p.bias + e.grp_off + gc0 + j) : 0.f;
+            if (rv_on) t += __ldg(rv + j);
+            v[j] += t;
+          }
       }
     }
     if (p.act) {
