@@ -337,6 +337,36 @@ def gpu_torch_baseline(torch, dev, n_steps: int = 3):
                       "timed and extrapolated to 50"}
 
 
+class Watchdog:
+    """A stalled phase must not cost the run its measured headline: past the deadline (DBIR_BENCH_DEADLINE_S, default
+    1500 s; a normal run takes 3-4 minutes) rank 0 prints the line with whatever has been measured so far plus
+    `"incomplete": <phase that never finished>` and every rank leaves the process."""
+
+    def __init__(self, rank: int):
+        self.rank, self.line, self.phase = rank, None, "start-up"
+        self.lock, self.done = threading.Lock(), False
+        self.deadline = float(os.environ.get("DBIR_BENCH_DEADLINE_S", "1500"))
+        threading.Thread(target=self._watch, daemon=True).start()
+
+    def _watch(self):
+        time.sleep(self.deadline)
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            log(f"[rank {self.rank}] bench deadline ({self.deadline:.0f} s) passed in phase '{self.phase}'")
+            if self.rank == 0 and self.line is not None:
+                print(json.dumps(dict(self.line, incomplete=self.phase)), flush=True)
+            os._exit(0 if self.line is not None else 3)
+
+    def finish(self, line):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            print(json.dumps(line), flush=True)
+
+
 def run_leg(name: str, limit_s: int):
     """`python bench.py --leg <name>` in a child process; its last stdout line is the leg's JSON object."""
     try:
@@ -388,6 +418,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     lib.load()
+    dog = Watchdog(rank)
     headline_tiled = args.workload == "tiled2048"
     t_build = time.time()
     pipe = build_synthetic_pipeline(dev, seed=1234)
@@ -456,6 +487,27 @@ def run_ours(args):
     value_512, e2e_512 = mpix_512 / (dev_ms / 1e3), mpix_512 / (e2e_ms / 1e3)
 
     log(f"[rank {rank}] 512^2 timed: {dev_ms / args.steps:.1f} ms per image")
+    wl_512 = "BSR pipeline 512x512, 50-step spaced sampler, cfg 4.0, random-init SD2.1 UNet+ControlNet (configs[1])"
+    line = {
+        "metric": METRIC, "value": value_512, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate" if lib.operand_dtype() == torch.float16 else "bf16 operands / f32 accumulate",
+        "data": "synthetic",
+        "config": {
+            "workload": wl_512, "images_per_gpu_per_step": 1, "sampler_steps": SAMPLER_STEPS,
+            "parallelism": "independent replicas, no collective (the sharded path with a collective is the tiled2048 block)",
+            "l2": "no flush needed: each forward streams 2.6 GB of weights >> 126 MB L2",
+        },
+        "e2e": {"value": e2e_512, "unit": "MPix/s", "h2d_bytes_per_step": int(lq.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "phases_ms": phases,
+        "batch4_512": None, "tiled2048": None, "v21_1024_b4": None, "roofline": None, "cpu_baseline": None,
+        "gpu_torch_baseline": None,
+    }
+    dog.line, dog.phase = line, "batch4_512"
     # ------------------------------------------------------------------ 512^2, four images per call (throughput mode)
     b4 = None
     if not args.no_batch4:
@@ -476,6 +528,7 @@ def run_ours(args):
                       "throughput mode of a folder run; the headline `value` keeps one image per call (latency mode)"}
 
     log(f"[rank {rank}] batch-4 block done")
+    line["batch4_512"], dog.phase = b4, "tiled2048"
     # ------------------------------------------------------------------ tiled 2048^2 (sharded, all-gather per step)
     tiled = None
     if not args.no_tiled:
@@ -535,6 +588,7 @@ def run_ours(args):
                              "CLIP replicated"}
 
     log(f"[rank {rank}] tiled-2048 block done")
+    line["tiled2048"], dog.phase = tiled, "v21_1024_b4"
     # ------------------------------------------------------------------ v2.1 1024^2 batch 4 (configs[4])
     v21 = None
     if not args.no_v21:
@@ -587,7 +641,9 @@ def run_ours(args):
                            "build is DBIR_OPERANDS=bf16)"}
 
     log(f"[rank {rank}] v2.1 block done")
+    line["v21_1024_b4"], dog.phase = v21, "roofline census"
     if rank != 0:
+        dog.done = True
         if world > 1:
             dist.destroy_process_group()
         return
@@ -635,6 +691,7 @@ def run_ours(args):
         for k, (fl, ms, n) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[0]},{'x'.join(map(str, k[1:]))},{n},{fl / 1e9:.2f},{ms:.4f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f}\n")
     log("[rank 0] kernel census done")
+    line["roofline"], dog.phase = roof, "baselines"
     # ---- baselines on the same box, N = 1 only ------------------------------------------------
     cpu = gpu_base = None
     if world == 1 and not args.no_cpu_baseline:
@@ -642,34 +699,11 @@ def run_ours(args):
         # (a cold cuDNN page-in took 6 minutes on one box) must not cost the line its measured numbers.
         del pipe
         torch.cuda.empty_cache()
-        gpu_base = run_leg("gpu_torch", 300)
+        gpu_base = run_leg("gpu_torch", 240)
         log(f"[rank 0] GPU torch baseline: {str(gpu_base)[:200]}")
-        cpu = run_leg("cpu", 420)
+        cpu = run_leg("cpu", 300)
         log(f"[rank 0] CPU baseline: {str(cpu)[:200]}")
-    wl_512 = "BSR pipeline 512x512, 50-step spaced sampler, cfg 4.0, random-init SD2.1 UNet+ControlNet (configs[1])"
-    line = {
-        "metric": METRIC, "value": value_512, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 operands / f32 accumulate" if lib.operand_dtype() == torch.float16 else "bf16 operands / f32 accumulate",
-        "data": "synthetic",
-        "config": {
-            "workload": wl_512, "images_per_gpu_per_step": 1, "sampler_steps": SAMPLER_STEPS,
-            "parallelism": "independent replicas, no collective (the sharded path with a collective is the tiled2048 block)",
-            "l2": "no flush needed: each forward streams 2.6 GB of weights >> 126 MB L2",
-        },
-        "e2e": {"value": e2e_512, "unit": "MPix/s", "h2d_bytes_per_step": int(lq.nbytes), "d2h_bytes_per_step": int(out.nbytes),
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches),
-        "clocks": clk,
-        "phases_ms": phases,
-        "batch4_512": b4,
-        "tiled2048": tiled,
-        "v21_1024_b4": v21,
-        "roofline": roof,
-        "cpu_baseline": cpu,
-        "gpu_torch_baseline": gpu_base,
-    }
+    line["cpu_baseline"], line["gpu_torch_baseline"] = cpu, gpu_base
     if headline_tiled and tiled is not None:
         line.update(metric="MPix/s end-to-end 50-step restore, tiled 2048px", value=tiled["value"],
                     ms_per_step=tiled["ms_per_image"], scaling="strong", e2e=tiled["e2e"],
@@ -677,7 +711,7 @@ def run_ours(args):
         line["config"]["workload"] = tiled["workload"]
         line["config"]["parallelism"] = "tiles sharded round-robin + all-gather"
         line["replicas512"] = {"value": value_512, "e2e": e2e_512, "ms_per_step": dev_ms / args.steps}
-    print(json.dumps(line))
+    dog.finish(line)
     if world > 1:
         dist.destroy_process_group()
 
