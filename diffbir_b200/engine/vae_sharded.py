@@ -22,8 +22,6 @@ against 130 + 90 ms of replicated encode + decode at 2048^2.
 """
 from __future__ import annotations
 
-from typing import List, Optional
-
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F

@@ -1,5 +1,6 @@
-"""-m gpu, >= 2 GPUs: tiled sampling sharded over NCCL ranks is bit-identical to single-rank tiled
-sampling and every rank holds the bit-identical latent (tools/run_tiled_multi.py under torchrun).
+"""-m gpu, >= 2 GPUs: (tile, CFG branch) and (image, CFG branch) units sharded over NCCL ranks are bit-identical
+to the single-rank run, every rank holds the bit-identical latent, and the row-sharded VAE agrees with the single-GPU
+engine to the fp16 noise floor (tools/run_tiled_multi.py under torchrun).
 On a 1-GPU box the multi-rank part cannot run; test_batch_invariance_single_gpu covers the property
 the sharded path relies on (a tile's eps does not depend on the batch it runs in)."""
 import subprocess
