@@ -199,3 +199,40 @@ def test_scunet_matches_reference(golden_dir):
         pipe = SCUNetPipeline(net, None, None, None, "cpu")
         a, b = pipe.apply_cleaner(x, False, 512, 256), osc.scunet_apply_cleaner(net, x)
         assert a.shape[2:] == (853, 512) and torch.equal(a, b)
+
+
+def test_whole_pipeline_matches_reference_run(golden_dir):
+    """The oracle's restatement of SwinIRPipeline.run (stage 1, resize, VAE encode, text tower, CFG sampler loop,
+    VAE decode, wavelet colour fix, resize back, uint8 truncation) against the uint8 output of the REFERENCE's own
+    `Pipeline.run` on the reduced networks (tests/golden/gen_golden_pipeline.py): spaced / eps and DDIM / v + zero SNR."""
+    from diffbir_b200.model import Diffusion
+    from diffbir_b200.model.clip import SyntheticTokenizer
+    from diffbir_b200.utils.synth import synthetic_sd_checkpoint
+    from tests.small_cfg import CLIP_SMALL
+    g = np.load(golden_dir / "pipeline_small.npz")
+    sd = synthetic_sd_checkpoint(UNET_SMALL, VAE_SMALL, CLIP_SMALL, 1234)
+    usd = {k[len("model.diffusion_model."):]: v for k, v in sd.items() if k.startswith("model.diffusion_model.")}
+    vsd = {k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")}
+    clipsd = {k[len("cond_stage_model.model."):]: v for k, v in sd.items() if k.startswith("cond_stage_model.model.")}
+    csd = make_state_dict(arch.unet_shapes(CN_SMALL, True), 1237, arch.is_zero_init)
+    ssd = make_state_dict(arch.swinir_shapes(SWIN_SMALL), 1238)
+    tok = SyntheticTokenizer(CLIP_SMALL["vocab_size"])
+    scales = {"s": [1.0] * 13}
+    neg = "low quality, blurry, low-resolution, noisy, unsharp, weird textures"
+    for sampler, steps, pname, zs in (("spaced", 3, "eps", False), ("ddim", 4, "v", True)):
+        d = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000, parameterization=pname, zero_snr=zs)
+        torch.manual_seed(231)
+        with torch.no_grad():
+            out = osm.swinir_pipeline_run(
+                g["lq"], cleaner=lambda im: osw.swinir_forward(ssd, im), encode_img=lambda im: ocl.vae_encode_mode(vsd, im, 0.18215),
+                encode_txt=lambda txt: ocl.clip_text_encode(clipsd, tok(txt), heads=CLIP_SMALL["heads"]),
+                decode=lambda z: ocl.vae_decode(vsd, z / 0.18215),
+                model=lambda x, t, c: ocl.cldm_forward(usd, csd, x, t, c["c_txt"], c["c_img"], scales["s"]),
+                betas=d.betas, parameterization=pname, steps=steps, strength=1.0, pos_prompt="a photo", neg_prompt=neg,
+                cfg_scale=4.0, sampler=sampler, set_strength=lambda s: scales.update(s=[s] * 13))
+        ref = g[f"out_{sampler}_{pname}"]
+        diff = np.abs(out.astype(int) - ref.astype(int))
+        mse = (diff.astype(np.float64) ** 2).mean()
+        psnr = float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+        print(f"whole pipeline {sampler}/{pname}: {100 * (diff > 0).mean():.3f} % of pixels differ, max |diff| {diff.max()}, PSNR {psnr:.1f} dB")
+        assert out.shape == ref.shape and diff.max() <= 1 and psnr > 70.0
