@@ -272,3 +272,22 @@ def test_small_bsrnet_pipeline_matches_oracle():
     print(f"small BSRNet pipeline x6: latent rel-rms {e:.2e}, uint8 PSNR {p:.1f} dB, output {out.shape}")
     assert out.shape == ref.shape == (1, 512, 640, 3) and out.dtype == np.uint8
     assert e < 2e-2 and p > 45.0
+
+
+def test_small_pipeline_vs_reference_whole_run(golden_dir):
+    """Product vs the REFERENCE itself, end to end: the uint8 output of the reference's SwinIRPipeline.run on the reduced
+    networks (tests/golden/pipeline_small.npz, produced on the CPU by gen_golden_pipeline.py) against Pipeline.run of
+    this package on the same weights, input and x_T. DDIM with eta = 0 consumes no per-step noise, so the CPU-drawn
+    x_T (first draw after the seed, pipeline.py:150-158) is the only randomness and can be injected."""
+    g = np.load(golden_dir / "pipeline_small.npz")
+    pipe = _pipe(True, v_prediction=True)
+    lq = g["lq"]
+    torch.manual_seed(231)
+    x_T = torch.randn((1, 4, 64, 88))                         # 96 x 128 -> short edge 512 -> 512 x 682 -> padded 512 x 704
+    kw = dict(RUN_DEFAULTS, steps=4, sampler_type="ddim", pos_prompt="a photo")
+    out = pipe.run(lq, **kw, x_T=x_T.cuda())
+    ref = g["out_ddim_v"]
+    p = _psnr_u8(out, ref)
+    print(f"product vs reference whole run (DDIM, v, zero SNR, reduced nets): uint8 PSNR {p:.1f} dB, "
+          f"differing pixels {(out != ref).mean() * 100:.1f}%, max |diff| {np.abs(out.astype(int) - ref.astype(int)).max()}")
+    assert out.shape == ref.shape and p > 45.0
