@@ -289,7 +289,8 @@ def swinir_pipeline_run(lq_u8: np.ndarray, cleaner: Callable, encode_img: Callab
                         x_T: Optional[torch.Tensor] = None,
                         noises: Optional[List[torch.Tensor]] = None, device="cpu",
                         set_strength: Optional[Callable] = None, taps: Optional[dict] = None,
-                        stage1: Optional[Callable] = None, out_size: Optional[Tuple[int, int]] = None):
+                        stage1: Optional[Callable] = None, out_size: Optional[Tuple[int, int]] = None,
+                        sample_fn: Optional[Callable] = None):
     """SwinIRPipeline.run (start_point 'noise', noise_aug 0, un-tiled VAE) —
     pipeline.py:235-321, 71-233, 371-397.  Callables stand for the networks:
     cleaner(img01)->img01, encode_img(img_pm1)->latent, encode_txt(list)->c_txt,
@@ -314,10 +315,14 @@ def swinir_pipeline_run(lq_u8: np.ndarray, cleaner: Callable, encode_img: Callab
         x_T = torch.randn((bs, 4, h2, w2), dtype=torch.float32, device=device)
     if set_strength is not None:
         set_strength(strength)
-    fn = spaced_sample if sampler == "spaced" else ddim_sample
-    z = fn(model, betas, parameterization, steps, x_T, cond, uncond, cfg_scale,
-           rescale_cfg=rescale_cfg, noises=noises, tiled=cldm_tiled,
-           tile_size=cldm_tile_size // 8, tile_stride=cldm_tile_stride // 8)
+    # sample_fn(model, x_T, cond, uncond) -> z: another sampler family's loop (pipeline.py:186-218 picks it by name)
+    if sample_fn is not None:
+        z = sample_fn(model, x_T, cond, uncond)
+    else:
+        fn = spaced_sample if sampler == "spaced" else ddim_sample
+        z = fn(model, betas, parameterization, steps, x_T, cond, uncond, cfg_scale,
+               rescale_cfg=rescale_cfg, noises=noises, tiled=cldm_tiled,
+               tile_size=cldm_tile_size // 8, tile_stride=cldm_tile_stride // 8)
     z = z[..., :h1, :w1]
     x = decode(z)[:, :, : clean.shape[2], : clean.shape[3]]
     if taps is not None:

@@ -76,6 +76,32 @@ def main():
                      RUN["s_tmin"], RUN["s_tmax"], RUN["s_noise"], RUN["eta"], RUN["order"])
         out[f"out_{sampler}_{pname}"] = y
         print(sampler, pname, y.shape, y.dtype, float(y.mean()), float(y.std()))
+    # The other two stage-1 pipelines with the two other sampler families (both step rules are noise-free, so a GPU run
+    # with the same x_T is comparable): BSRNetPipeline (x4 RRDBNet, pipeline.py:324-366) + EDM dpm++_2m on the v / zero-SNR
+    # model, SCUNetPipeline (pipeline.py:400-421) + DPM-Solver++ multistep order 2 on the eps model.
+    from diffbir.model.bsrnet import RRDBNet
+    from diffbir.model.scunet import SCUNet
+    from tests.small_cfg import RRDB_SMALL, SCUNET_SMALL
+    rr = RRDBNet(**RRDB_SMALL).eval()
+    rr.load_state_dict(make_state_dict(arch.rrdbnet_shapes(RRDB_SMALL), 91), strict=True)
+    sc = SCUNet(in_nc=SCUNET_SMALL["in_nc"], config=list(SCUNET_SMALL["config"]), dim=SCUNET_SMALL["dim"]).eval()
+    sc.load_state_dict(make_state_dict(arch.scunet_shapes(SCUNET_SMALL), 9), strict=True)
+    lq2 = synthetic_lq(128, 160, seed=3)
+    out["lq_bsr"] = lq2
+    for tag, sampler, steps, pname, zs in (("bsrnet", "edm_dpm++_2m", 6, "v", True), ("scunet", "dpm++_m2", 6, "eps", False)):
+        diffusion = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000, parameterization=pname, zero_snr=zs)
+        if tag == "bsrnet":
+            pipe, img = rpipe.BSRNetPipeline(rr, cldm, diffusion, None, "cpu", 4.0), lq2
+        else:
+            pipe, img = rpipe.SCUNetPipeline(sc, cldm, diffusion, None, "cpu"), lq
+        torch.manual_seed(231)
+        y = pipe.run(img, steps, RUN["strength"], RUN["cleaner_tiled"], RUN["cleaner_tile_size"], RUN["cleaner_tile_stride"],
+                     RUN["vae_encoder_tiled"], RUN["vae_encoder_tile_size"], RUN["vae_decoder_tiled"], RUN["vae_decoder_tile_size"],
+                     RUN["cldm_tiled"], RUN["cldm_tile_size"], RUN["cldm_tile_stride"], RUN["pos_prompt"], RUN["neg_prompt"],
+                     RUN["cfg_scale"], RUN["start_point_type"], sampler, RUN["noise_aug"], RUN["rescale_cfg"], RUN["s_churn"],
+                     RUN["s_tmin"], RUN["s_tmax"], RUN["s_noise"], RUN["eta"], RUN["order"])
+        out[f"out_{tag}"] = y
+        print(tag, sampler, pname, y.shape, y.dtype, float(y.mean()), float(y.std()))
     np.savez_compressed(OUT / "pipeline_small.npz", **out)
     print("wrote pipeline_small.npz")
 

@@ -274,20 +274,37 @@ def test_small_bsrnet_pipeline_matches_oracle():
     assert e < 2e-2 and p > 45.0
 
 
-def test_small_pipeline_vs_reference_whole_run(golden_dir):
-    """Product vs the REFERENCE itself, end to end: the uint8 output of the reference's SwinIRPipeline.run on the reduced
-    networks (tests/golden/pipeline_small.npz, produced on the CPU by gen_golden_pipeline.py) against Pipeline.run of
-    this package on the same weights, input and x_T. DDIM with eta = 0 consumes no per-step noise, so the CPU-drawn
-    x_T (first draw after the seed, pipeline.py:150-158) is the only randomness and can be injected."""
+@pytest.mark.parametrize("case", ["swinir_ddim", "bsrnet_edm", "scunet_dpm"])
+def test_small_pipeline_vs_reference_whole_run(golden_dir, case):
+    """Product vs the REFERENCE itself, end to end: the uint8 output of the reference's {SwinIR,BSRNet,SCUNet}Pipeline.run
+    on the reduced networks (tests/golden/pipeline_small.npz, produced on the CPU by gen_golden_pipeline.py) against the
+    same pipeline class of this package on the same weights, input and x_T. The three samplers (DDIM eta 0, EDM dpm++_2m,
+    DPM-Solver++ m2) consume no per-step noise, so the CPU-drawn x_T (first draw after the seed, pipeline.py:150-158) is
+    the only randomness and can be injected."""
+    from diffbir_b200.model import RRDBNet, SCUNet
+    from diffbir_b200.pipeline import BSRNetPipeline, SCUNetPipeline
+    from tests.small_cfg import RRDB_SMALL, SCUNET_SMALL
     g = np.load(golden_dir / "pipeline_small.npz")
-    pipe = _pipe(True, v_prediction=True)
-    lq = g["lq"]
+    if case == "swinir_ddim":
+        pipe = _pipe(True, v_prediction=True)
+        lq, ref, L, kw = g["lq"], g["out_ddim_v"], (64, 88), dict(steps=4, sampler_type="ddim")     # 96 x 128 -> 512 x 683 -> padded 512 x 704
+    elif case == "bsrnet_edm":
+        p0 = _pipe(True, v_prediction=True)
+        net = RRDBNet(**RRDB_SMALL, device="cuda")
+        net.load_state_dict(make_state_dict(arch.rrdbnet_shapes(RRDB_SMALL), 91))
+        pipe = BSRNetPipeline(net, p0.cldm, p0.diffusion, None, "cuda", upscale=4.0)
+        lq, ref, L, kw = g["lq_bsr"], g["out_bsrnet"], (64, 80), dict(steps=6, sampler_type="edm_dpm++_2m")
+    else:
+        p0 = _pipe(True, v_prediction=False)
+        net = SCUNet(**SCUNET_SMALL, device="cuda")
+        net.load_state_dict(make_state_dict(arch.scunet_shapes(SCUNET_SMALL), 9))
+        pipe = SCUNetPipeline(net, p0.cldm, p0.diffusion, None, "cuda")
+        lq, ref, L, kw = g["lq"], g["out_scunet"], (64, 88), dict(steps=6, sampler_type="dpm++_m2")
+    pipe.taps = {}
     torch.manual_seed(231)
-    x_T = torch.randn((1, 4, 64, 88))                         # 96 x 128 -> short edge 512 -> 512 x 682 -> padded 512 x 704
-    kw = dict(RUN_DEFAULTS, steps=4, sampler_type="ddim", pos_prompt="a photo")
-    out = pipe.run(lq, **kw, x_T=x_T.cuda())
-    ref = g["out_ddim_v"]
+    x_T = torch.randn((1, 4) + L)
+    out = pipe.run(lq, **dict(RUN_DEFAULTS, pos_prompt="a photo", **kw), x_T=x_T.cuda())
     p = _psnr_u8(out, ref)
-    print(f"product vs reference whole run (DDIM, v, zero SNR, reduced nets): uint8 PSNR {p:.1f} dB, "
+    print(f"product vs reference whole run [{case}] (reduced nets): uint8 PSNR {p:.1f} dB, "
           f"differing pixels {(out != ref).mean() * 100:.1f}%, max |diff| {np.abs(out.astype(int) - ref.astype(int)).max()}")
     assert out.shape == ref.shape and p > 45.0

@@ -236,3 +236,56 @@ def test_whole_pipeline_matches_reference_run(golden_dir):
         psnr = float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
         print(f"whole pipeline {sampler}/{pname}: {100 * (diff > 0).mean():.3f} % of pixels differ, max |diff| {diff.max()}, PSNR {psnr:.1f} dB")
         assert out.shape == ref.shape and diff.max() <= 1 and psnr > 70.0
+
+
+def test_whole_bsrnet_and_scunet_pipelines_match_reference_run(golden_dir):
+    """The two other stage-1 pipelines with the two other sampler families, end to end against the reference's own
+    uint8 output: BSRNetPipeline + EDM dpm++_2m (v, zero SNR) and SCUNetPipeline + DPM-Solver++ m2 (eps). Networks are
+    the oracle's; the sampler loops are the product's host code (itself bit-exact vs the reference, test_host_logic.py)
+    driving the oracle network on the CPU."""
+    from diffbir_b200.model import Diffusion
+    from diffbir_b200.model.clip import SyntheticTokenizer
+    from diffbir_b200.sampler import DPMSolverSampler, EDMSampler
+    from diffbir_b200.utils.synth import synthetic_sd_checkpoint
+    from oracle import bsrnet as ob
+    from oracle import scunet as osc
+    from tests.small_cfg import CLIP_SMALL, RRDB_SMALL, SCUNET_SMALL
+    g = np.load(golden_dir / "pipeline_small.npz")
+    sd = synthetic_sd_checkpoint(UNET_SMALL, VAE_SMALL, CLIP_SMALL, 1234)
+    usd = {k[len("model.diffusion_model."):]: v for k, v in sd.items() if k.startswith("model.diffusion_model.")}
+    vsd = {k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")}
+    clipsd = {k[len("cond_stage_model.model."):]: v for k, v in sd.items() if k.startswith("cond_stage_model.model.")}
+    csd = make_state_dict(arch.unet_shapes(CN_SMALL, True), 1237, arch.is_zero_init)
+    rsd = make_state_dict(arch.rrdbnet_shapes(RRDB_SMALL), 91)
+    scsd = make_state_dict(arch.scunet_shapes(SCUNET_SMALL), 9)
+    tok = SyntheticTokenizer(CLIP_SMALL["vocab_size"])
+    neg = "low quality, blurry, low-resolution, noisy, unsharp, weird textures"
+    cases = (("bsrnet", "lq_bsr", "edm_dpm++_2m", "v", True, (512, 640),
+              lambda im: ob.bsrnet_apply_cleaner(lambda t: ob.rrdbnet_forward(rsd, t), im, 4.0)),
+             ("scunet", "lq", "dpm++_m2", "eps", False, None,
+              lambda im: osc.scunet_apply_cleaner(lambda t: osc.scunet_forward(scsd, t), im)))
+    for tag, lqk, sampler, pname, zs, out_size, stage1 in cases:
+        d = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000, parameterization=pname, zero_snr=zs)
+
+        def sample_fn(model, x_T, cond, uncond):
+            if sampler.startswith("edm"):
+                smp = EDMSampler(d.betas, pname, False, sampler, 0, 0, 300, 1, 1, 1)
+            else:
+                smp = DPMSolverSampler(d.betas, pname, False, sampler)
+            return smp.sample(model, "cpu", 6, tuple(x_T.shape), cond, uncond, 4.0, x_T=x_T, progress=False)
+
+        torch.manual_seed(231)
+        with torch.no_grad():
+            out = osm.swinir_pipeline_run(
+                g[lqk], cleaner=None, encode_img=lambda im: ocl.vae_encode_mode(vsd, im, 0.18215),
+                encode_txt=lambda txt: ocl.clip_text_encode(clipsd, tok(txt), heads=CLIP_SMALL["heads"]),
+                decode=lambda z: ocl.vae_decode(vsd, z / 0.18215),
+                model=lambda x, t, c: ocl.cldm_forward(usd, csd, x, t, c["c_txt"], c["c_img"], [1.0] * 13),
+                betas=d.betas, parameterization=pname, steps=6, strength=1.0, pos_prompt="a photo", neg_prompt=neg,
+                cfg_scale=4.0, stage1=stage1, out_size=out_size, sample_fn=sample_fn)
+        ref = g[f"out_{tag}"]
+        diff = np.abs(out.astype(int) - ref.astype(int))
+        mse = (diff.astype(np.float64) ** 2).mean()
+        psnr = float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+        print(f"whole {tag} pipeline {sampler}/{pname}: {100 * (diff > 0).mean():.3f} % of pixels differ, max |diff| {diff.max()}, PSNR {psnr:.1f} dB")
+        assert out.shape == ref.shape and diff.max() <= 1 and psnr > 70.0
