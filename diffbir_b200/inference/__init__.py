@@ -1,8 +1,9 @@
 """diffbir.inference counterpart: the inference loops whose networks are on the accelerated path.
-Unaligned faces (face detector) and custom loops are refused by the CLI."""
+The unaligned-face loop (face detector) is refused by the CLI."""
 from .bfr_loop import BFRInferenceLoop
 from .bid_loop import BIDInferenceLoop
 from .bsr_loop import BSRInferenceLoop
+from .custom_loop import CustomInferenceLoop
 from .loop import InferenceLoop
 
-__all__ = ["InferenceLoop", "BSRInferenceLoop", "BFRInferenceLoop", "BIDInferenceLoop"]
+__all__ = ["InferenceLoop", "BSRInferenceLoop", "BFRInferenceLoop", "BIDInferenceLoop", "CustomInferenceLoop"]

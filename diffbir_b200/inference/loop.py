@@ -94,8 +94,6 @@ def check_supported(args: Namespace) -> None:
         raise NotImplementedError("--precision fp32: the kernels take 16-bit operands (fp32 accumulate / residual stream)")
     if args.vae_encoder_tiled or args.vae_decoder_tiled:
         raise NotImplementedError("Tiled-VAE is outside the path (SURVEY.md §8f); the VAE engines run un-tiled")
-    if args.version == "custom":
-        raise NotImplementedError("--version custom (CustomInferenceLoop): load the networks with the model classes directly")
 
 
 class InferenceLoop:

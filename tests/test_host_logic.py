@@ -261,7 +261,8 @@ def test_diffbir_alias_exposes_the_reference_names():
     assert dm.RRDBNet is diffbir_b200.model.RRDBNet and dp.BSRNetPipeline is diffbir_b200.pipeline.BSRNetPipeline
     assert dm.SCUNet is diffbir_b200.model.SCUNet and dp.SCUNetPipeline is diffbir_b200.pipeline.SCUNetPipeline
     assert di.BIDInferenceLoop is diffbir_b200.inference.BIDInferenceLoop
-    for cls in (di.UnAlignedBFRInferenceLoop, di.CustomInferenceLoop, dm.ControlNet):
+    assert di.CustomInferenceLoop is diffbir_b200.inference.CustomInferenceLoop
+    for cls in (di.UnAlignedBFRInferenceLoop, dm.ControlNet):
         with pytest.raises(NotImplementedError):
             cls()
     # the YAML reflection targets of the reference configs resolve through the alias too

@@ -39,8 +39,7 @@ def test_cli_has_every_reference_flag_with_its_default(tmp_path):
 
 @pytest.mark.parametrize("extra,msg", [(["--captioner", "llava"], "captioner"),
                                         (["--guidance"], "guidance"), (["--precision", "fp32"], "fp32"),
-                                        (["--device", "cpu"], "CUDA"), (["--vae_decoder_tiled"], "Tiled-VAE"),
-                                        (["--version", "custom"], "custom")])
+                                        (["--device", "cpu"], "CUDA"), (["--vae_decoder_tiled"], "Tiled-VAE")])
 def test_options_outside_the_path_are_refused(tmp_path, extra, msg):
     with pytest.raises(NotImplementedError, match=msg):
         loop_mod.check_supported(args_for(tmp_path, *extra))
@@ -149,3 +148,55 @@ def test_load_checkpoint_with_foreign_pickled_globals(tmp_path):
         del sys.modules["fake_lightning_callbacks"]
     sd = load_checkpoint(str(path))
     assert list(sd) == ["w"] and torch.equal(sd["w"], torch.arange(6.0).view(2, 3))
+
+
+def test_custom_loop_reads_the_training_yaml(tmp_path, monkeypatch):
+    """CustomInferenceLoop (custom_loop.py:19-93): networks from the training YAML's model block, weights from its train
+    block + --ckpt, SwinIRPipeline, bicubic pre-upscale. Model construction needs the GPU library, so the reflection and
+    the checkpoint reader are recorded instead."""
+    import yaml
+    from diffbir_b200.inference import custom_loop as cl
+    with pytest.raises(ValueError, match="train_cfg"):
+        cl.CustomInferenceLoop(args_for(tmp_path, "--version", "custom"))
+    cfg = dict(model=dict(cldm=dict(target="diffbir.model.cldm.ControlLDM", params=dict(latent_scale_factor=0.18215)),
+                          swinir=dict(target="diffbir.model.swinir.SwinIR", params=dict(img_size=64)),
+                          diffusion=dict(target="diffbir.model.gaussian_diffusion.Diffusion", params=dict(parameterization="v"))),
+               train=dict(sd_path=str(tmp_path / "sd.ckpt"), swinir_path=str(tmp_path / "swinir.ckpt")))
+    (tmp_path / "train.yaml").write_text(yaml.safe_dump(cfg))
+    events = []
+
+    class Net:
+        def __init__(self, kind):
+            self.kind = kind
+
+        def load_pretrained_sd(self, sd):
+            events.append(("sd", sd))
+            return [], []
+
+        def load_controlnet_from_ckpt(self, sd):
+            events.append(("controlnet", sd))
+
+        def load_state_dict(self, sd, strict=True):
+            events.append(("swinir", sd, strict))
+
+    def fake_instantiate(config, **extra):
+        events.append(("new", config["target"], dict(config.get("params", {})), extra))
+        return Net(config["target"])
+
+    monkeypatch.setattr(cl, "instantiate_from_config", fake_instantiate)
+    monkeypatch.setattr(cl, "load_checkpoint", lambda path: f"<{Path(path).name}>")
+    monkeypatch.setattr(cl.CustomInferenceLoop, "_operand_check", lambda self: None)
+    args = args_for(tmp_path, "--version", "custom", "--train_cfg", str(tmp_path / "train.yaml"), "--ckpt",
+                    str(tmp_path / "controlnet.pt"), "--upscale", "2")
+    lp = cl.CustomInferenceLoop(args)
+    assert [e[:2] for e in events] == [("new", "diffbir.model.swinir.SwinIR"), ("swinir", "<swinir.ckpt>"),
+                                       ("new", "diffbir.model.cldm.ControlLDM"), ("sd", "<sd.ckpt>"),
+                                       ("controlnet", "<controlnet.pt>"), ("new", "diffbir.model.gaussian_diffusion.Diffusion")]
+    assert events[1][2] is True and events[0][3] == {"device": "cuda"} and events[2][3]["synthetic_tokenizer"] is False
+    assert type(lp.pipeline).__name__ == "SwinIRPipeline" and lp.pipeline.cleaner.kind.endswith("SwinIR")
+    assert lp.after_load_lq(Image.new("RGB", (30, 20))).shape == (40, 60, 3)
+    # an empty train.sd_path (the shipped training YAML leaves it blank) is reported, not passed to torch.load
+    cfg["train"]["sd_path"] = None
+    (tmp_path / "train.yaml").write_text(yaml.safe_dump(cfg))
+    with pytest.raises(ValueError, match="train.sd_path"):
+        cl.CustomInferenceLoop(args)
