@@ -77,11 +77,13 @@ def test_cldm_small_vs_oracle_shapes(L, nb):
     assert e < TOL
 
 
-def test_cldm_full_config_vs_oracle():
+def test_cldm_full_config_vs_oracle(golden_dir):
     """SD-2.1 UNet + ControlNet (1.23 B parameters, random init), latent 64x64, batch 2 (the
-    cond/uncond pair of one 512x512 image) against the fp32 oracle."""
+    cond/uncond pair of one 512x512 image) against the fp32 oracle, and against the output of the REFERENCE's own
+    modules on the same weights and inputs (tests/golden/full_config.npz, gen_golden_full.py)."""
     from oracle import cldm as ocl
     no_tf32()
+    g = np.load(golden_dir / "full_config.npz")
     eng, usd, csd = _cldm_engine(arch.UNET_CFG, arch.CONTROLNET_CFG, seeds=(1234, 1235))
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(1, 4, 64, 64, generator=gen).repeat(2, 1, 1, 1).cuda()
@@ -97,8 +99,9 @@ def test_cldm_full_config_vs_oracle():
         with torch.no_grad():
             ref = ocl.cldm_forward(usd_d, csd_d, x, torch.full((2,), t, device="cuda"), ctx, hint, scales)
         e = rel_rms(eps, ref)
-        print(f"cldm full t={t}: rel rms {e:.2e}, psnr {psnr(eps, ref):.1f} dB, |eps| {ref.abs().mean():.3f}")
-        assert e < TOL
+        eg = rel_rms(eps, torch.from_numpy(g[f"cldm_eps_t{t}"]).cuda())
+        print(f"cldm full t={t}: rel rms {e:.2e}, psnr {psnr(eps, ref):.1f} dB, |eps| {ref.abs().mean():.3f}; vs reference fixture {eg:.2e}")
+        assert e < TOL and eg < TOL
 
 
 def test_vae_small_vs_reference_golden(golden_dir):
@@ -113,10 +116,11 @@ def test_vae_small_vs_reference_golden(golden_dir):
     assert e1 < TOL and e2 < TOL
 
 
-def test_vae_full_config_vs_oracle():
+def test_vae_full_config_vs_oracle(golden_dir):
     from diffbir_b200.engine.vae import VaeEngine
     from oracle import cldm as ocl
     no_tf32()
+    g = np.load(golden_dir / "full_config.npz")
     sd = make_state_dict(arch.vae_shapes(arch.VAE_CFG), 77)
     eng = VaeEngine(sd, None, "cuda")
     sd_d = to_dev(sd)
@@ -128,8 +132,11 @@ def test_vae_full_config_vs_oracle():
     with torch.no_grad():
         rdec, rmom = ocl.vae_decode(sd_d, z), ocl.vae_encode_moments(sd_d, img)
     e1, e2 = rel_rms(dec, rdec), rel_rms(mom, rmom)
-    print(f"vae full: decode {e1:.2e} ({psnr(dec, rdec):.1f} dB) encode {e2:.2e}")
-    assert e1 < TOL and e2 < TOL
+    st = int(g["vae_dec_stride"])
+    g1 = rel_rms(dec[..., ::st, ::st], torch.from_numpy(g["vae_dec"]).cuda())
+    g2 = rel_rms(mom, torch.from_numpy(g["vae_moments"]).cuda())
+    print(f"vae full: decode {e1:.2e} ({psnr(dec, rdec):.1f} dB) encode {e2:.2e}; vs reference fixture {g1:.2e} / {g2:.2e}")
+    assert e1 < TOL and e2 < TOL and g1 < TOL and g2 < TOL
 
 
 def test_swinir_small_vs_reference_golden(golden_dir):
@@ -147,7 +154,7 @@ def test_swinir_small_vs_reference_golden(golden_dir):
 
 
 @pytest.mark.parametrize("size", [256, 512])
-def test_swinir_full_config_vs_oracle(size):
+def test_swinir_full_config_vs_oracle(size, golden_dir):
     from diffbir_b200.engine.swinir import SwinIREngine
     from oracle import swinir as osw
     no_tf32()
@@ -160,6 +167,11 @@ def test_swinir_full_config_vs_oracle(size):
     err = ((y - ref).abs().max() / ref.std()).item()
     print(f"swinir {size}: max err / std = {err:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB")
     assert err < 3e-2
+    if size == 256:                                            # the reference's own output for this weight / input pair
+        gref = torch.from_numpy(np.load(golden_dir / "full_config.npz")["swinir_y256"]).cuda()
+        eg = ((y - gref).abs().max() / gref.std()).item()
+        print(f"swinir 256 vs reference fixture: max err / std = {eg:.2e}")
+        assert eg < 3e-2
 
 
 def test_rrdbnet_small_vs_reference_golden(golden_dir):
@@ -176,8 +188,9 @@ def test_rrdbnet_small_vs_reference_golden(golden_dir):
     assert torch.equal(y, eng.forward(torch.from_numpy(g["x"]).cuda()))        # graph replay: same bits
 
 
-def test_rrdbnet_full_config_vs_oracle():
-    """BSRNet (23 RRDB, configs/inference/bsrnet.yaml) on a 128x160 LQ image -> 512x640, against the fp32 oracle."""
+def test_rrdbnet_full_config_vs_oracle(golden_dir):
+    """BSRNet (23 RRDB, configs/inference/bsrnet.yaml) on a 128x160 LQ image -> 512x640, against the fp32 oracle and the
+    reference's own output (full_config.npz)."""
     from diffbir_b200.engine.bsrnet import RRDBNetEngine
     from oracle import bsrnet as ob
     no_tf32()
@@ -188,8 +201,11 @@ def test_rrdbnet_full_config_vs_oracle():
     with torch.no_grad():
         ref = ob.rrdbnet_forward(to_dev(sd), x)
     e = rel_rms(y, ref)
-    print(f"rrdbnet full: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB, |y| {ref.abs().mean():.4f}")
-    assert y.shape == (1, 3, 512, 640) and e < TOL
+    g = np.load(golden_dir / "full_config.npz")
+    st = int(g["rrdb_stride"])
+    eg = rel_rms(y[..., ::st, ::st], torch.from_numpy(g["rrdb_y"]).cuda())
+    print(f"rrdbnet full: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB, |y| {ref.abs().mean():.4f}; vs reference fixture {eg:.2e}")
+    assert y.shape == (1, 3, 512, 640) and e < TOL and eg < TOL
 
 
 def test_scunet_small_vs_reference_golden(golden_dir):
@@ -207,8 +223,9 @@ def test_scunet_small_vs_reference_golden(golden_dir):
     assert torch.equal(y, net(torch.from_numpy(g["x"]).cuda()))
 
 
-def test_scunet_full_config_vs_oracle():
-    """SCUNet [4,4,4,4,4,4,4] x dim 64 (configs/inference/scunet.yaml) on a 256 x 320 image against the fp32 oracle."""
+def test_scunet_full_config_vs_oracle(golden_dir):
+    """SCUNet [4,4,4,4,4,4,4] x dim 64 (configs/inference/scunet.yaml) on a 256 x 320 image against the fp32 oracle and the
+    reference's own output (full_config.npz)."""
     from diffbir_b200.engine.scunet import SCUNetEngine
     from oracle import scunet as osc
     no_tf32()
@@ -219,5 +236,8 @@ def test_scunet_full_config_vs_oracle():
     with torch.no_grad():
         ref = osc.scunet_forward(to_dev(sd), x)
     e = rel_rms(y, ref)
-    print(f"scunet full: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB, |y| {ref.abs().mean():.4f}")
-    assert y.shape == x.shape and e < TOL
+    g = np.load(golden_dir / "full_config.npz")
+    st = int(g["scunet_stride"])
+    eg = rel_rms(y[..., ::st, ::st], torch.from_numpy(g["scunet_y"]).cuda())
+    print(f"scunet full: rel rms {e:.2e}, psnr(peak 1) {psnr(y, ref, 1.0):.1f} dB, |y| {ref.abs().mean():.4f}; vs reference fixture {eg:.2e}")
+    assert y.shape == x.shape and e < TOL and eg < TOL

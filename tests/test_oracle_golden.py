@@ -289,3 +289,49 @@ def test_whole_bsrnet_and_scunet_pipelines_match_reference_run(golden_dir):
         psnr = float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
         print(f"whole {tag} pipeline {sampler}/{pname}: {100 * (diff > 0).mean():.3f} % of pixels differ, max |diff| {diff.max()}, PSNR {psnr:.1f} dB")
         assert out.shape == ref.shape and diff.max() <= 1 and psnr > 70.0
+
+
+def _rel_rms(a, b):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+
+
+def test_full_config_oracle_matches_reference(golden_dir):
+    """The oracle at FULL width (real SD-2.1 UNet + ControlNet, full VAE / SwinIR / RRDBNet / SCUNet of
+    configs/inference/*.yaml) against outputs of the reference's own modules on the weights and inputs of the full-config
+    GPU tests (tests/golden/gen_golden_full.py): the reference == oracle == CUDA chain is closed at full width too."""
+    from oracle import bsrnet as ob
+    from oracle import scunet as osc
+    g = np.load(golden_dir / "full_config.npz")
+    res = {}
+    with torch.no_grad():
+        usd = make_state_dict(arch.unet_shapes(arch.UNET_CFG), 1234, arch.is_zero_init)
+        csd = make_state_dict(arch.unet_shapes(arch.CONTROLNET_CFG, True), 1235, arch.is_zero_init)
+        gen = torch.Generator().manual_seed(0)
+        x = torch.randn(1, 4, 64, 64, generator=gen).repeat(2, 1, 1, 1)
+        hint = (torch.randn(1, 4, 64, 64, generator=gen) * 0.5).repeat(2, 1, 1, 1)
+        ctx = torch.randn(2, 77, 1024, generator=gen)
+        eps = ocl.cldm_forward(usd, csd, x, torch.full((2,), 500), ctx, hint, [1.0] * 13)
+        res["cldm t=500"] = _rel_rms(eps, g["cldm_eps_t500"])
+        eps = ocl.cldm_forward(usd, csd, x[:1], torch.full((1,), 0), ctx[:1], hint[:1], [1.0] * 13)      # one row of the t = 0 case
+        res["cldm t=0 row 0"] = _rel_rms(eps, g["cldm_eps_t0"][:1])
+        del usd, csd
+        vsd = make_state_dict(arch.vae_shapes(arch.VAE_CFG), 77)
+        gen = torch.Generator().manual_seed(31)
+        z16 = torch.randn(1, 4, 16, 16, generator=gen)
+        img128 = torch.rand(1, 3, 128, 128, generator=gen) * 2 - 1
+        res["vae decode 16"] = _rel_rms(ocl.vae_decode(vsd, z16), g["vae_dec16"])
+        res["vae encode 128"] = _rel_rms(ocl.vae_encode_moments(vsd, img128), g["vae_moments128"])
+        ssd = make_state_dict(arch.swinir_shapes(arch.SWINIR_CFG), 1234)
+        xs = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(0))
+        res["swinir 256"] = _rel_rms(osw.swinir_forward(ssd, xs), g["swinir_y256"])
+        rsd = make_state_dict(arch.rrdbnet_shapes(arch.RRDBNET_CFG), 78)
+        xr = torch.rand(1, 3, 128, 160, generator=torch.Generator().manual_seed(4))
+        s = int(g["rrdb_stride"])
+        res["rrdbnet 128x160"] = _rel_rms(ob.rrdbnet_forward(rsd, xr)[..., ::s, ::s], g["rrdb_y"])
+        scsd = make_state_dict(arch.scunet_shapes(arch.SCUNET_CFG), 79)
+        xc = torch.rand(1, 3, 256, 320, generator=torch.Generator().manual_seed(6))
+        s = int(g["scunet_stride"])
+        res["scunet 256x320"] = _rel_rms(osc.scunet_forward(scsd, xc)[..., ::s, ::s], g["scunet_y"])
+    print("full-config oracle vs reference (rel. RMS): " + ", ".join(f"{k} {v:.1e}" for k, v in res.items()))
+    assert max(res.values()) < 2e-5, res
