@@ -8,6 +8,7 @@ import re
 import subprocess
 import sys
 
+HBM_PEAK_GBS = 6574.5      # MEASURED_PEAKS.json (copy bandwidth on this pool's B200s)
 WANT = {
     "gpu__time_duration.sum": "dur",
     "sm__inst_executed_pipe_tensor.sum.pct_of_peak_sustained_active": "tensor_inst_pct",
@@ -62,7 +63,7 @@ def main(rep, out):
         gbs = dram / (d.get("dur", float("nan")) * 1e-6) / 1e9 if d.get("dur") else float("nan")
         res[-1]["dram_gbs"] = gbs
         lines.append(f"{name[:44]:44s} grid {d['grid']:>16s} {d.get('dur', 0):8.1f} us  tensor-pipe {tensor:5.1f}%  "
-                     f"dram {d.get('dram_r', 0) / 1e6:7.1f}+{d.get('dram_w', 0) / 1e6:6.1f} MB = {gbs:6.0f} GB/s ({d.get('dram_pct', 0):4.1f}% of peak)  "
+                     f"dram {d.get('dram_r', 0) / 1e6:7.1f}+{d.get('dram_w', 0) / 1e6:6.1f} MB = {gbs:6.0f} GB/s ({100 * gbs / HBM_PEAK_GBS:4.1f}% of the measured {HBM_PEAK_GBS:.0f} GB/s)  "
                      f"L2->SM {l2sm / 1e6:7.1f} MB  L2 hit {d.get('l2_hit', 0):4.1f}%  regs {int(d.get('regs', 0))}  "
                      f"smem {d.get('smem', 0) / 1e3:.1f} KB  warps active {d.get('occ_pct', 0):4.1f}%")
     open(out + ".json", "w").write(json.dumps(res, indent=1))
