@@ -206,17 +206,18 @@ def make_tiled_fn(model: Callable, size: int, stride: int) -> Callable:
     return tiled
 
 
-def make_tiled_image_fn(fn: Callable, size: int, stride: int) -> Callable:
-    """Image version (scale 1, Gaussian weights) of utils/common.py:172-232, as used by the tiled
-    stage-1 branch (pipeline.py:389-394): row-major windows, accumulate fn(tile) * w and w, divide."""
+def make_tiled_image_fn(fn: Callable, size: int, stride: int, scale: int = 1) -> Callable:
+    """Image version (Gaussian weights; scale 1, or an up-scaling `fn` with scale_type "up") of utils/common.py:172-232,
+    as used by the tiled stage-1 branches (pipeline.py:389-394, 349-357): row-major windows, accumulate fn(tile) * w and
+    w, divide."""
     def tiled(x):
         b, c, h, w = x.shape
-        out = torch.zeros_like(x)
-        count = torch.zeros_like(x, dtype=torch.float32)
-        wts = torch.tensor(gaussian_weights(size, size)[None, None], dtype=x.dtype, device=x.device)
+        out = torch.zeros((b, c, h * scale, w * scale), dtype=x.dtype, device=x.device)
+        count = torch.zeros_like(out, dtype=torch.float32)
+        wts = torch.tensor(gaussian_weights(size * scale, size * scale)[None, None], dtype=x.dtype, device=x.device)
         for hi, he, wi, we in sliding_windows(h, w, size, stride):
-            out[..., hi:he, wi:we] += fn(x[..., hi:he, wi:we]) * wts
-            count[..., hi:he, wi:we] += wts
+            out[..., hi * scale:he * scale, wi * scale:we * scale] += fn(x[..., hi:he, wi:we]) * wts
+            count[..., hi * scale:he * scale, wi * scale:we * scale] += wts
         return out / count
     return tiled
 

@@ -26,6 +26,11 @@ def stand_in(t: torch.Tensor) -> torch.Tensor:
     return torch.tanh(t) * 0.5 + t.mean(dim=(2, 3), keepdim=True) * 0.25
 
 
+def stand_in_up4(t: torch.Tensor) -> torch.Tensor:
+    """A x4 up-scaler whose output depends on the whole tile."""
+    return torch.nn.functional.interpolate(stand_in(t), scale_factor=4, mode="bilinear", align_corners=False)
+
+
 @torch.no_grad()
 def main():
     import diffbir.pipeline as P
@@ -51,6 +56,20 @@ def main():
     out["cleaner_tiled_128_64_sub8"] = full[..., ::8, ::8].numpy()
     out["cleaner_tiny_untiled_shape"] = np.array(tiny.shape)
     out["cleaner_tiny_untiled_sub8"] = tiny[..., ::8, ::8].numpy()
+    # x4 up-scaling tiles (make_tiled_fn(scale_type="up", scale=4), utils/common.py:196-205) and the tiled branches of the
+    # two other stage-1 pipelines: BSRNetPipeline.apply_cleaner (pipeline.py:342-366) in both output-size regimes,
+    # SCUNetPipeline.apply_cleaner (pipeline.py:402-421)
+    out["tiled_up4_24_16_sub4"] = make_tiled_fn(stand_in_up4, size=24, stride=16, scale_type="up", scale=4, progress=False)(x)[..., ::4, ::4].numpy()
+    for scale, key in ((2.0, "bsr_tiled_small"), (4.0, "bsr_tiled_big")):
+        bp = P.BSRNetPipeline(stand_in_up4, None, None, None, "cpu", scale)
+        bp.set_output_size(lq.size())
+        y = bp.apply_cleaner(lq, True, 64, 48)
+        out[key + "_shape"] = np.array(y.shape)
+        out[key + "_sub8"] = y[..., ::8, ::8].numpy()
+    sp = P.SCUNetPipeline(stand_in, None, None, None, "cpu")
+    y = sp.apply_cleaner(lq, True, 64, 48)
+    out["scunet_tiled_shape"] = np.array(y.shape)
+    out["scunet_tiled_sub8"] = y[..., ::8, ::8].numpy()
     np.savez_compressed(OUT / "tiled_fn.npz", **out)
     print({k: v.shape for k, v in out.items()})
 

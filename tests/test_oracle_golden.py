@@ -132,6 +132,24 @@ def test_tiled_image_fn_and_tiled_cleaner_match_reference():
             np.testing.assert_array_equal(out[..., ::8, ::8].numpy(), g[name + "_sub8"])
     with pytest.raises(ValueError):
         pipe.apply_cleaner(torch.zeros(1, 3, 256, 256), True, 100, 50)
+    # x4 up-scaling tiles and the tiled branches of BSRNetPipeline (both output-size regimes) and SCUNetPipeline
+    from diffbir_b200.pipeline import BSRNetPipeline, SCUNetPipeline
+
+    def stand_in_up4(t):
+        return torch.nn.functional.interpolate(stand_in(t), scale_factor=4, mode="bilinear", align_corners=False)
+
+    ref = g["tiled_up4_24_16_sub4"]
+    np.testing.assert_array_equal(make_tiled_fn(stand_in_up4, 24, 16, scale_type="up", scale=4)(x)[..., ::4, ::4].numpy(), ref)
+    np.testing.assert_array_equal(osm.make_tiled_image_fn(stand_in_up4, 24, 16, scale=4)(x)[..., ::4, ::4].numpy(), ref)
+    for scale, key in ((2.0, "bsr_tiled_small"), (4.0, "bsr_tiled_big")):
+        bp = BSRNetPipeline(stand_in_up4, None, None, None, "cpu", upscale=scale)
+        bp.set_output_size(lq.size())
+        y = bp.apply_cleaner(lq, True, 64, 48)
+        assert tuple(y.shape) == tuple(g[key + "_shape"])
+        np.testing.assert_array_equal(y[..., ::8, ::8].numpy(), g[key + "_sub8"])
+    y = SCUNetPipeline(stand_in, None, None, None, "cpu").apply_cleaner(lq, True, 64, 48)
+    assert tuple(y.shape) == tuple(g["scunet_tiled_shape"])
+    np.testing.assert_array_equal(y[..., ::8, ::8].numpy(), g["scunet_tiled_sub8"])
 
 
 def test_clip_text_tower_matches_reference(golden_dir):
