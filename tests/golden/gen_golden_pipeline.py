@@ -102,6 +102,24 @@ def main():
                      RUN["s_tmin"], RUN["s_tmax"], RUN["s_noise"], RUN["eta"], RUN["order"])
         out[f"out_{tag}"] = y
         print(tag, sampler, pname, y.shape, y.dtype, float(y.mean()), float(y.std()))
+    # The optional branches of Pipeline.apply_cldm / apply_cleaner: start point "cond" + noise augmentation of the
+    # condition (pipeline.py:146-167), control strength 0.7 (:173-174), the cosine CFG ramp; and both tiled modes
+    # (Gaussian-blended SwinIR tiles, mixture-of-diffusers latent tiles).
+    for tag, sampler, steps, pname, zs, over in (
+            ("opts", "spaced", 3, "eps", False, dict(start_point_type="cond", noise_aug=40, rescale_cfg=True, strength=0.7)),
+            ("tiled", "ddim", 4, "v", True, dict(cleaner_tiled=True, cleaner_tile_size=64, cleaner_tile_stride=32, cldm_tiled=True,
+                                                  cldm_tile_size=512, cldm_tile_stride=256))):
+        r = dict(RUN, **over)
+        diffusion = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000, parameterization=pname, zero_snr=zs)
+        pipe = rpipe.SwinIRPipeline(swin, cldm, diffusion, None, "cpu")
+        torch.manual_seed(231)
+        y = pipe.run(lq, steps, r["strength"], r["cleaner_tiled"], r["cleaner_tile_size"], r["cleaner_tile_stride"],
+                     r["vae_encoder_tiled"], r["vae_encoder_tile_size"], r["vae_decoder_tiled"], r["vae_decoder_tile_size"],
+                     r["cldm_tiled"], r["cldm_tile_size"], r["cldm_tile_stride"], r["pos_prompt"], r["neg_prompt"],
+                     r["cfg_scale"], r["start_point_type"], sampler, r["noise_aug"], r["rescale_cfg"], r["s_churn"],
+                     r["s_tmin"], r["s_tmax"], r["s_noise"], r["eta"], r["order"])
+        out[f"out_{tag}"] = y
+        print(tag, sampler, pname, y.shape, y.dtype, float(y.mean()), float(y.std()))
     np.savez_compressed(OUT / "pipeline_small.npz", **out)
     print("wrote pipeline_small.npz")
 

@@ -353,3 +353,77 @@ def test_full_config_oracle_matches_reference(golden_dir):
         res["scunet 256x320"] = _rel_rms(osc.scunet_forward(scsd, xc)[..., ::s, ::s], g["scunet_y"])
     print("full-config oracle vs reference (rel. RMS): " + ", ".join(f"{k} {v:.1e}" for k, v in res.items()))
     assert max(res.values()) < 2e-5, res
+
+
+class _OracleCldm:
+    """The ControlLDM surface Pipeline.apply_cldm and the samplers use (prepare_condition_pair, vae_decode,
+    control_scales, the model call), backed by the oracle networks on the CPU: lets the PRODUCT's pipeline / sampler host
+    code run without the GPU library."""
+
+    def __init__(self, usd, csd, vsd, clipsd, tok, heads):
+        self.usd, self.csd, self.vsd, self.clipsd, self.tok, self.heads = usd, csd, vsd, clipsd, tok, heads
+        self.control_scales = [1.0] * 13
+        self.shard_vae = False
+
+    def _txt(self, prompts):
+        return ocl.clip_text_encode(self.clipsd, self.tok(prompts), heads=self.heads)
+
+    def prepare_condition_pair(self, cond_img, pos, neg):
+        c_img = ocl.vae_encode_mode(self.vsd, cond_img * 2 - 1, 0.18215)
+        return dict(c_txt=self._txt(pos), c_img=c_img), dict(c_txt=self._txt(neg), c_img=c_img.clone())
+
+    def vae_decode(self, z):
+        return ocl.vae_decode(self.vsd, z / 0.18215)
+
+    def __call__(self, x, t, cond):
+        return ocl.cldm_forward(self.usd, self.csd, x, t, cond["c_txt"], cond["c_img"], self.control_scales)
+
+
+def test_product_pipeline_host_code_matches_reference_run(golden_dir):
+    """The PRODUCT's Pipeline.run / apply_cleaner / apply_cldm and sampler classes (the host code that ships), with the
+    oracle networks plugged in where the kernel engines sit, against the uint8 output of whole runs of the reference:
+    all three pipeline classes, all four sampler families, incl. the RNG draw order (x_T, per-step noise), the optional
+    branches (start point "cond", noise augmentation, control strength, CFG ramp) and both tiled modes."""
+    from diffbir_b200.model import Diffusion
+    from diffbir_b200.model.clip import SyntheticTokenizer
+    from diffbir_b200.pipeline import BSRNetPipeline, SCUNetPipeline, SwinIRPipeline
+    from diffbir_b200.utils.synth import RUN_DEFAULTS, synthetic_sd_checkpoint
+    from oracle import bsrnet as ob
+    from oracle import scunet as osc
+    from tests.small_cfg import CLIP_SMALL, RRDB_SMALL, SCUNET_SMALL
+    g = np.load(golden_dir / "pipeline_small.npz")
+    sd = synthetic_sd_checkpoint(UNET_SMALL, VAE_SMALL, CLIP_SMALL, 1234)
+    part = lambda pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}      # noqa: E731
+    cldm = _OracleCldm(part("model.diffusion_model."), make_state_dict(arch.unet_shapes(CN_SMALL, True), 1237, arch.is_zero_init),
+                       part("first_stage_model."), part("cond_stage_model.model."), SyntheticTokenizer(CLIP_SMALL["vocab_size"]),
+                       CLIP_SMALL["heads"])
+    ssd = make_state_dict(arch.swinir_shapes(SWIN_SMALL), 1238)
+    rsd = make_state_dict(arch.rrdbnet_shapes(RRDB_SMALL), 91)
+    scsd = make_state_dict(arch.scunet_shapes(SCUNET_SMALL), 9)
+    swin = lambda im: osw.swinir_forward(ssd, im)                  # noqa: E731
+    cases = (("out_spaced_eps", "lq", "spaced", 3, "eps", False, lambda d: SwinIRPipeline(swin, cldm, d, None, "cpu")),
+             ("out_ddim_v", "lq", "ddim", 4, "v", True, lambda d: SwinIRPipeline(swin, cldm, d, None, "cpu")),
+             ("out_bsrnet", "lq_bsr", "edm_dpm++_2m", 6, "v", True,
+              lambda d: BSRNetPipeline(lambda im: ob.rrdbnet_forward(rsd, im), cldm, d, None, "cpu", upscale=4.0)),
+             ("out_scunet", "lq", "dpm++_m2", 6, "eps", False,
+              lambda d: SCUNetPipeline(lambda im: osc.scunet_forward(scsd, im), cldm, d, None, "cpu")))
+    cases = tuple(c + ({},) for c in cases) + (
+        # optional branches: start point "cond", noise-augmented condition, control strength, cosine CFG ramp
+        ("out_opts", "lq", "spaced", 3, "eps", False, lambda d: SwinIRPipeline(swin, cldm, d, None, "cpu"),
+         dict(start_point_type="cond", noise_aug=40, rescale_cfg=True, strength=0.7)),
+        # both tiled modes: Gaussian-blended stage-1 tiles, mixture-of-diffusers latent tiles
+        ("out_tiled", "lq", "ddim", 4, "v", True, lambda d: SwinIRPipeline(swin, cldm, d, None, "cpu"),
+         dict(cleaner_tiled=True, cleaner_tile_size=64, cleaner_tile_stride=32, cldm_tiled=True, cldm_tile_size=512, cldm_tile_stride=256)))
+    for key, lqk, sampler, steps, pname, zs, make, over in cases:
+        pipe = make(Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000, parameterization=pname, zero_snr=zs))
+        torch.manual_seed(231)
+        with torch.no_grad():
+            out = pipe.run(g[lqk], **dict(RUN_DEFAULTS, steps=steps, sampler_type=sampler, pos_prompt="a photo", **over))
+        ref = g[key]
+        diff = np.abs(out.astype(int) - ref.astype(int))
+        mse = (diff.astype(np.float64) ** 2).mean()
+        psnr = float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+        print(f"product host code, {type(pipe).__name__} + {sampler}/{pname} {over or ''}: {100 * (diff > 0).mean():.3f} % of pixels differ, "
+              f"max |diff| {diff.max()}, PSNR {psnr:.1f} dB")
+        assert out.shape == ref.shape and diff.max() <= 1 and psnr > 70.0
+        assert cldm.control_scales == [1.0] * 13            # restored after the run (pipeline.py:232)
