@@ -94,3 +94,57 @@ def wavelet_reconstruction(content_feat: torch.Tensor, style_feat: torch.Tensor)
     ch, _ = wavelet_decomposition(content_feat)
     _, sl = wavelet_decomposition(style_feat)
     return ch + sl
+
+
+def load_file_from_url(url: str, model_dir=None, progress: bool = True, file_name=None) -> str:
+    """utils/common.py:81-110 without the download: the file the URL names (or `file_name`) must already be in
+    `model_dir` (default: $DIFFBIR_WEIGHTS_DIR or ./weights) — there is no network access on this path."""
+    import os
+    from urllib.parse import urlparse
+    from ..inference.pretrained_models import default_weights_dir
+    model_dir = default_weights_dir() if model_dir is None else model_dir
+    path = os.path.abspath(os.path.join(model_dir, file_name or os.path.basename(urlparse(url).path)))
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not found: place the file of {url} there (downloads are not performed)")
+    return path
+
+
+def load_model_from_url(url: str):
+    """utils/common.py:113-120: the checkpoint behind a registry URL (or bare file name) as a flat state_dict
+    (`state_dict` wrapper and `module.` prefix removed), read from the local weights directory."""
+    from ..inference.loop import load_checkpoint
+    return load_checkpoint(load_file_from_url(url))
+
+
+class VRAMPeakMonitor:
+    """utils/common.py:261-280: context manager around a loading / inference phase; prints the peak allocation when
+    DIFFBIR_TRACE_VRAM=1 (the reference's TRACE_VRAM switch). Works without a CUDA device (then it does nothing)."""
+
+    def __init__(self, tag: str) -> None:
+        self.tag = tag
+
+    def __enter__(self):
+        self.peak_before = torch.cuda.max_memory_allocated() / 1024 ** 3 if torch.cuda.is_available() else 0.0
+        return self
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        import os
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+            if os.environ.get("DIFFBIR_TRACE_VRAM", "0") == "1":
+                peak_after = torch.cuda.max_memory_allocated() / 1024 ** 3
+                print(f"\033[93mVRAM peak before {self.tag}: {self.peak_before:.2f} GB, after: {peak_after:.2f} GB\033[0m")
+        return False
+
+
+def to(obj, device):
+    """utils/common.py:310-319: moves the tensors of a nested dict / tuple / list."""
+    if torch.is_tensor(obj):
+        return obj.to(device)
+    if isinstance(obj, dict):
+        return {k: to(v, device) for k, v in obj.items()}
+    if isinstance(obj, tuple):
+        return tuple(to(v, device) for v in obj)
+    if isinstance(obj, list):
+        return [to(v, device) for v in obj]
+    return obj

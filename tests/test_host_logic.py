@@ -265,6 +265,15 @@ def test_diffbir_alias_exposes_the_reference_names():
     for cls in (di.UnAlignedBFRInferenceLoop, dm.ControlNet):
         with pytest.raises(NotImplementedError):
             cls()
+    # run_gradio.py-style helpers: registry + local "download", VRAM monitor, nested .to()
+    from diffbir.inference.pretrained_models import MODELS
+    from diffbir.utils.common import VRAMPeakMonitor, load_model_from_url, to
+    assert set(MODELS) >= {"sd_v2.1", "v2.1", "swinir_general", "bsrnet", "scunet_psnr"}
+    with pytest.raises(FileNotFoundError, match="v2.pth"):
+        load_model_from_url("https://example.invalid/some/path/" + MODELS["v2"])
+    with VRAMPeakMonitor("phase"):
+        moved = to(dict(a=torch.ones(2), b=[torch.zeros(1), "s"], c=(torch.ones(1),)), "cpu")
+    assert moved["b"][1] == "s" and isinstance(moved["c"], tuple) and torch.equal(moved["a"], torch.ones(2))
     # the YAML reflection targets of the reference configs resolve through the alias too
     from diffbir.model.cldm import ControlLDM
     from diffbir.model.gaussian_diffusion import Diffusion

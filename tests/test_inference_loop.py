@@ -200,3 +200,16 @@ def test_custom_loop_reads_the_training_yaml(tmp_path, monkeypatch):
     (tmp_path / "train.yaml").write_text(yaml.safe_dump(cfg))
     with pytest.raises(ValueError, match="train.sd_path"):
         cl.CustomInferenceLoop(args)
+
+
+def test_load_model_from_url_reads_the_local_file(tmp_path, monkeypatch):
+    """utils/common.py:113-120 semantics on a local weights directory: `state_dict` wrapper and `module.` prefix removed."""
+    import torch
+    from diffbir_b200.utils.common import load_file_from_url, load_model_from_url
+    monkeypatch.setenv("DIFFBIR_WEIGHTS_DIR", str(tmp_path))
+    torch.save({"state_dict": {"module.a.weight": torch.arange(3.0), "module.b": torch.ones(1)}}, tmp_path / "v2.pth")
+    sd = load_model_from_url("https://huggingface.co/org/repo/resolve/main/" + MODELS["v2"])
+    assert list(sd) == ["a.weight", "b"] and torch.equal(sd["a.weight"], torch.arange(3.0))
+    assert load_file_from_url("whatever/x.bin", model_dir=str(tmp_path), file_name="v2.pth").endswith("v2.pth")
+    with pytest.raises(FileNotFoundError, match="downloads are not performed"):
+        load_file_from_url("https://host/none.ckpt")
