@@ -92,7 +92,9 @@ def check_supported(args: Namespace) -> None:
         raise NotImplementedError("--guidance: restoration guidance is not wired into the reference's samplers either")
     if args.precision == "fp32":
         raise NotImplementedError("--precision fp32: the kernels take 16-bit operands (fp32 accumulate / residual stream)")
-    if args.vae_encoder_tiled or args.vae_decoder_tiled:
+    # stage-2 images are at least 512 on both sides, so a tile of 512 or less always tiles; larger tiles are left to the
+    # pipeline, which (like the reference) runs un-tiled when the image is smaller than a tile
+    if (args.vae_encoder_tiled and args.vae_encoder_tile_size <= 512) or (args.vae_decoder_tiled and args.vae_decoder_tile_size <= 512):
         raise NotImplementedError("Tiled-VAE is outside the path (SURVEY.md §8f); the VAE engines run un-tiled")
 
 

@@ -78,10 +78,18 @@ class Pipeline:
                    sampler_type, noise_aug, rescale_cfg, s_churn, s_tmin, s_tmax, s_noise, eta,
                    order, x_T: Optional[torch.Tensor] = None) -> torch.Tensor:
         """pipeline.py:71-233."""
-        if vae_encoder_tiled or vae_decoder_tiled:
-            raise NotImplementedError("tiled VAE is outside the B200 hot path (180 GB HBM per GPU)")
         bs, _, h0, w0 = cond_img.shape
-        cond_img = pad_to_multiples_of(cond_img, multiple=8 if cldm_tiled else 64)
+        cond_img = pad_to_multiples_of(cond_img, multiple=64 if not vae_encoder_tiled and not cldm_tiled else 8)
+        # Tiled-VAE itself is outside the path (180 GB of HBM), but the reference switches it off for inputs smaller than
+        # a tile (pipeline.py:106-110, 219-223) and then only the padding rule above differs: that branch is honoured.
+        if vae_encoder_tiled and (cond_img.size(2) < vae_encoder_tile_size or cond_img.size(3) < vae_encoder_tile_size):
+            print("[VAE Encoder]: the input size is tiny and unnecessary to tile.")
+            vae_encoder_tiled = False
+        if vae_decoder_tiled and (cond_img.size(2) // 8 < vae_decoder_tile_size // 8 or cond_img.size(3) // 8 < vae_decoder_tile_size // 8):
+            print("[VAE Decoder]: the input size is tiny and unnecessary to tile.")
+            vae_decoder_tiled = False
+        if vae_encoder_tiled or vae_decoder_tiled:
+            raise NotImplementedError("tiled VAE is outside the B200 hot path (180 GB HBM per GPU): the VAE engines run un-tiled")
         # ranks that cooperate on this job (sharded tiles or batch units) also shard the VAE by image rows
         import torch.distributed as dist
         coop = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and (cldm_tiled or self.shard_batch)

@@ -107,6 +107,9 @@ def main():
     # (Gaussian-blended SwinIR tiles, mixture-of-diffusers latent tiles).
     for tag, sampler, steps, pname, zs, over in (
             ("opts", "spaced", 3, "eps", False, dict(start_point_type="cond", noise_aug=40, rescale_cfg=True, strength=0.7)),
+            # Tiled-VAE flags with tiles larger than the image: the reference runs the VAE un-tiled but pads to 8, not 64 (:100-110)
+            ("vaetiny", "spaced", 3, "eps", False, dict(vae_encoder_tiled=True, vae_encoder_tile_size=1024, vae_decoder_tiled=True,
+                                                         vae_decoder_tile_size=1024)),
             ("tiled", "ddim", 4, "v", True, dict(cleaner_tiled=True, cleaner_tile_size=64, cleaner_tile_stride=32, cldm_tiled=True,
                                                   cldm_tile_size=512, cldm_tile_stride=256))):
         r = dict(RUN, **over)

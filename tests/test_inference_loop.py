@@ -44,6 +44,8 @@ def test_options_outside_the_path_are_refused(tmp_path, extra, msg):
     with pytest.raises(NotImplementedError, match=msg):
         loop_mod.check_supported(args_for(tmp_path, *extra))
     loop_mod.check_supported(args_for(tmp_path))          # the defaults are runnable
+    # VAE tiles larger than any 512-class input: the reference runs un-tiled then (pipeline.py:106-110), so does the pipeline
+    loop_mod.check_supported(args_for(tmp_path, "--vae_decoder_tiled", "--vae_decoder_tile_size", "4096"))
 
 
 def test_checkpoints_resolve_locally_and_fail_loudly(tmp_path):

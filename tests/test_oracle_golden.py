@@ -411,6 +411,9 @@ def test_product_pipeline_host_code_matches_reference_run(golden_dir):
         # optional branches: start point "cond", noise-augmented condition, control strength, cosine CFG ramp
         ("out_opts", "lq", "spaced", 3, "eps", False, lambda d: SwinIRPipeline(swin, cldm, d, None, "cpu"),
          dict(start_point_type="cond", noise_aug=40, rescale_cfg=True, strength=0.7)),
+        # Tiled-VAE flags with tiles larger than the image: un-tiled VAE, but the condition is padded to 8 instead of 64
+        ("out_vaetiny", "lq", "spaced", 3, "eps", False, lambda d: SwinIRPipeline(swin, cldm, d, None, "cpu"),
+         dict(vae_encoder_tiled=True, vae_encoder_tile_size=1024, vae_decoder_tiled=True, vae_decoder_tile_size=1024)),
         # both tiled modes: Gaussian-blended stage-1 tiles, mixture-of-diffusers latent tiles
         ("out_tiled", "lq", "ddim", 4, "v", True, lambda d: SwinIRPipeline(swin, cldm, d, None, "cpu"),
          dict(cleaner_tiled=True, cleaner_tile_size=64, cleaner_tile_stride=32, cldm_tiled=True, cldm_tile_size=512, cldm_tile_stride=256)))
