@@ -176,7 +176,11 @@ def cpu_reference_times(n_steps: int = 1, warm: int = 0, size: int = 512):
         ctx = torch.randn(1, 77, 1024)
         tt = torch.full((1,), 999)
         steps = []
+        budget_s = float(os.environ.get("DBIR_REF_BUDGET_S", "150"))      # bounded sample: stop early once >= 3 steps are in
+        loop0 = time.perf_counter()
         for i in range(warm + n_steps):
+            if len(steps) >= 3 and time.perf_counter() - loop0 > budget_s:
+                break
             t0 = time.perf_counter()
             ec = ocl.cldm_forward(usd, csd, xt, tt, ctx, c_img, [1.0] * 13)
             eu = ocl.cldm_forward(usd, csd, xt, tt, ctx, c_img, [1.0] * 13)
@@ -202,7 +206,7 @@ def run_reference(args):
     total = cpu_image_seconds(t, step_s)
     mpix = 512 * 512 / 1e6 / total
     sample = (f"oracle port of the reference (fp32, {cores} threads): SwinIR 512^2 {t['swinir']:.2f}s, VAE encode "
-              f"{t['vae_encode']:.2f}s (x2), decode {t['vae_decode']:.2f}s measured once; {args.steps} of 50 sampler "
+              f"{t['vae_encode']:.2f}s (x2), decode {t['vae_decode']:.2f}s measured once; {len(t['sampler_step'])} of 50 sampler "
               f"steps measured (median {step_s:.2f}s, 2 forwards each), image time extrapolated to 50 steps")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": "MPix/s", "n_gpus": args.gpus,
