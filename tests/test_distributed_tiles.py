@@ -82,6 +82,13 @@ def test_two_rank_tile_sharding_matches_single_process():
     assert sum(counts) == 2 * results[0][2] and counts[1] - counts[0] <= 1
 
 
+def test_four_rank_tile_sharding_matches_single_process():
+    """The N = 4 point of the driver's scaling run (only N = 2 and N = 8 ran on GPUs during development)."""
+    results = _run_world(4, 24, 40)
+    counts = sorted(n for _, _, _, n in results)
+    assert sum(counts) == 2 * results[0][2] and counts[-1] - counts[0] <= 1
+
+
 def test_fewer_tiles_than_ranks():
     """T < world (e.g. a 768^2 image on 8 GPUs): ranks without a tile send a zero buffer, still join
     the all-gather, and every rank blends the same result (used to dead-lock)."""
@@ -124,7 +131,7 @@ def _unit_worker(rank, world, port, q, B):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,B", [(2, 4), (3, 4), (3, 1)])
+@pytest.mark.parametrize("world,B", [(2, 4), (3, 4), (3, 1), (4, 4), (8, 4)])     # (4, 4) / (8, 4): configs[4] at N = 4 / 8
 def test_batch_unit_sharding_matches_single_process(world, B):
     """(CFG branch, image) units round-robin over the ranks + padded all-gather == the un-sharded batch,
     including U not divisible by world and U < world (ranks without a unit still join the collective)."""
