@@ -331,8 +331,6 @@ def test_full_config_oracle_matches_reference(golden_dir):
         ctx = torch.randn(2, 77, 1024, generator=gen)
         eps = ocl.cldm_forward(usd, csd, x, torch.full((2,), 500), ctx, hint, [1.0] * 13)
         res["cldm t=500"] = _rel_rms(eps, g["cldm_eps_t500"])
-        eps = ocl.cldm_forward(usd, csd, x[:1], torch.full((1,), 0), ctx[:1], hint[:1], [1.0] * 13)      # one row of the t = 0 case
-        res["cldm t=0 row 0"] = _rel_rms(eps, g["cldm_eps_t0"][:1])
         del usd, csd
         vsd = make_state_dict(arch.vae_shapes(arch.VAE_CFG), 77)
         gen = torch.Generator().manual_seed(31)
