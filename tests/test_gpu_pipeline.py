@@ -153,6 +153,26 @@ def test_full_config_50_step_ddim():
     assert p >= 50.0, f"PSNR {p:.2f} dB < 50 dB vs the fp32 reference path"
 
 
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes were spent: never run on a GPU yet, so it must "
+                                        "not be able to stop the suite (expected: XPASS at the PSNR of the test above)")
+def test_full_config_50_step_ddim_vs_reference_whole_run(golden_dir):
+    """BASELINE configs[2] against the REFERENCE itself: tests/golden/full_pipeline_ddim.npz is the uint8 output of the
+    reference's SwinIRPipeline.run at the full configuration (gen_golden_full_pipeline.py: same weights, image, prompts,
+    50-step DDIM, cfg 4.0, seed 231, CPU fp32). DDIM with eta 0 draws no per-step noise, so feeding the CPU-drawn x_T makes
+    the two runs comparable: the north star's "PSNR >= 50 dB vs reference output" without the oracle in between."""
+    g = np.load(golden_dir / "full_pipeline_ddim.npz")
+    pipe = _pipe(False)
+    lq = synthetic_lq(512, 512, seed=3)
+    torch.manual_seed(231)
+    x_T = torch.randn((1, 4, 64, 64))
+    out = pipe.run(lq, **dict(RUN_DEFAULTS, sampler_type="ddim"), x_T=x_T.cuda())
+    ref = g["out"]
+    p = _psnr_u8(out, ref)
+    print(f"FULL 512^2 50-step DDIM vs the reference's own run: uint8 PSNR {p:.2f} dB, differing pixels {(out != ref).mean() * 100:.1f}%, "
+          f"max |diff| {np.abs(out.astype(int) - ref.astype(int)).max()}")
+    assert out.shape == ref.shape and p >= 50.0
+
+
 def test_full_config_tiled_1024():
     """BASELINE configs[3] at 1024^2 (the fp32 oracle of 2048^2 x 49 tiles takes too long for a test):
     full SD-2.1 config, latent 128^2 -> 9 tiles of 64^2 (stride 32), 5 steps, Gaussian-blended in the
